@@ -1,0 +1,175 @@
+/*
+ * b2icp.h — C ABI of the Blackwell-native ICP scan-matching engine (libb2icp.so).
+ *
+ * This is the drop-in boundary for the hot path of YoshuaNava/icpslam.  The reference has no
+ * FFI seam: it builds a PCL registration object on the stack and calls it directly
+ * (reference src/icpslam/icp_odometer.cpp:188-201, src/icpslam/octree_mapper.cpp:104-117).
+ * Every entry point below names the reference lines (or the PCL call made from them) that it
+ * replaces.  All symbols are extern "C", take plain pointers and sizes, never throw, and return
+ * 0 on success or a negative b2icp_status.  Clouds are arrays of 16-byte points {x,y,z,w}
+ * (layout-identical to pcl::PointXYZ, so `reinterpret_cast<const float*>(cloud->points.data())`
+ * is a zero-copy argument).  The 4th float is ignored on input and written as 1.0f on output,
+ * exactly as pcl::Registration::align / setInputSource force data[3] = 1.
+ *
+ * Matrices: every 4x4 in this ABI is ROW-MAJOR (T[4*r+c]); p_target = T * p_source.
+ *
+ * Threading: calls on one handle are serialised by an internal mutex; distinct handles are
+ * independent (own CUDA stream).  All entry points are synchronous (results are in the caller's
+ * buffers on return) because the reference consumes T immediately (icp_odometer.cpp:199-206).
+ *
+ * There is NO CPU backend behind these symbols: without a CUDA device b2icp_create fails with
+ * B2ICP_ERR_CUDA.  (The CPU restatement under oracle/ is test infrastructure only.)
+ */
+#ifndef B2ICP_H_
+#define B2ICP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2ICP_VERSION_MAJOR 0
+#define B2ICP_VERSION_MINOR 1
+
+typedef struct b2icp_handle b2icp_handle;
+
+/* Error codes (returned negative). PCL prints PCL_ERROR and leaves converged_=false; we return. */
+typedef enum b2icp_status {
+  B2ICP_OK = 0,
+  B2ICP_ERR_INVALID_ARG = -1,
+  B2ICP_ERR_EMPTY_CLOUD = -2,                /* setInputSource rejects an empty cloud (PCL gicp.h) */
+  B2ICP_ERR_TOO_FEW_POINTS = -3,             /* N < k_correspondences: PCL computeCovariances bails out */
+  B2ICP_ERR_NOT_ENOUGH_CORRESPONDENCES = -4, /* < 3 (P2P) / < 4 (GICP) matches: converged=false */
+  B2ICP_ERR_SOLVER_FAILED = -5,
+  B2ICP_ERR_NONFINITE_INPUT = -6,
+  B2ICP_ERR_CUDA = -7,
+  B2ICP_ERR_NO_TARGET = -8,
+  B2ICP_ERR_NO_SOURCE = -9,
+  B2ICP_ERR_NOT_ALIGNED = -10                /* fitness / correspondences requested before align */
+} b2icp_status;
+
+/* Per-iteration solver. */
+typedef enum b2icp_mode {
+  /* pcl::IterativeClosestPoint pipeline (header included at octree_mapper.cpp:8): 1-NN,
+   * keep d^2 <= max^2, Umeyama/SVD, in-place float transform, DefaultConvergenceCriteria.
+   * This is the pipeline BASELINE.json's north_star spells out. */
+  B2ICP_MODE_P2P_SVD = 0,
+  /* pcl::GeneralizedIterativeClosestPoint — what the reference instantiates
+   * (icp_odometer.cpp:188, octree_mapper.cpp:104): k=20 covariances, Mahalanobis, BFGS. */
+  B2ICP_MODE_GICP_BFGS = 1
+} b2icp_mode;
+
+/* Presets for b2icp_default_params: the two constant blocks of the reference. */
+typedef enum b2icp_preset {
+  B2ICP_PRESET_ODOMETER = 0, /* include/icpslam/icp_odometer.h:62-65  (10 iterations) */
+  B2ICP_PRESET_MAPPER = 1    /* include/icpslam/octree_mapper.h:53-56 (30 iterations) */
+} b2icp_preset;
+
+typedef struct b2icp_params {
+  int32_t mode;                       /* b2icp_mode */
+  int32_t max_iterations;             /* setMaximumIterations: 10 odometer / 30 mapper */
+  double transformation_epsilon;      /* setTransformationEpsilon: 1e-6 */
+  double max_correspondence_distance; /* setMaxCorrespondenceDistance: 1.0 m */
+  double euclidean_fitness_epsilon;   /* PCL default -DBL_MAX (never set by the reference) */
+  double rotation_epsilon;            /* GICP default 2e-3 */
+  double gicp_epsilon;                /* GICP default 1e-3 */
+  int32_t k_correspondences;          /* GICP default 20 */
+  int32_t max_inner_iterations;       /* GICP default 20 */
+  int32_t device;                     /* CUDA device ordinal */
+  int32_t profile;                    /* !=0: record CUDA events around every nn_sweep launch */
+  float grid_cell;                    /* neighbour-grid cell edge in metres; <=0 = auto */
+  int32_t reserved[5];
+} b2icp_params;
+
+typedef struct b2icp_result {
+  double T[16];          /* getFinalTransformation().cast<double>() — row-major, source -> target */
+  int32_t converged;     /* hasConverged() */
+  int32_t iterations;    /* outer iterations executed (nr_iterations_) */
+  int32_t n_corr_last;   /* correspondences that passed the distance gate in the last iteration */
+  int32_t status_detail; /* b2icp_status of the solver loop (0, NOT_ENOUGH_CORRESPONDENCES, ...) */
+  double mse_last;       /* mean gated d^2 of the last iteration (DefaultConvergenceCriteria's MSE) */
+  double fitness;        /* NaN unless filled by b2icp_align_fitness / b2icp_fitness */
+} b2icp_result;
+
+/* Accumulated device timings of the last b2icp_align on this handle (profile != 0). */
+typedef struct b2icp_timing {
+  int32_t nn_sweep_launches; /* launches of the fused nn_sweep kernel */
+  int32_t reserved;
+  double nn_sweep_ms;        /* sum of their CUDA-event durations */
+  double build_ms;           /* grid build of source/target done inside align (0 if cached) */
+  double total_ms;           /* first launch -> last launch of align, CUDA events */
+  uint64_t nn_candidates;    /* candidate points examined by the last profiled sweep set */
+  uint64_t nt_touched;       /* N_t' : target points inside cells touched by the last sweep */
+} b2icp_timing;
+
+/* Fill `p` with the reference's constants for one of its two call sites. */
+int b2icp_default_params(b2icp_params* p, int preset);
+
+/* Lifetime of what the reference does with `GeneralizedIterativeClosestPoint icp;` on the stack
+ * (icp_odometer.cpp:188-192, octree_mapper.cpp:104-108: ctor + the four set* calls). */
+int b2icp_create(const b2icp_params* p, b2icp_handle** out);
+int b2icp_destroy(b2icp_handle* h);
+/* Change solver parameters on a live handle (keeps device buffers). */
+int b2icp_set_params(b2icp_handle* h, const b2icp_params* p);
+
+/* icp.setInputTarget(prev_cloud_) (icp_odometer.cpp:194, octree_mapper.cpp:110) + the k-d tree
+ * build PCL does inside align(): uploads the cloud and builds the neighbour grid. */
+int b2icp_set_target(b2icp_handle* h, const float* xyzw, size_t n);
+/* icp.setInputSource(curr_cloud_) (icp_odometer.cpp:193, octree_mapper.cpp:109). */
+int b2icp_set_source(b2icp_handle* h, const float* xyzw, size_t n);
+/* Same, for clouds that already live in device memory of the handle's device
+ * (device-resident pipelines and the HBM-resident leg of bench.py). */
+int b2icp_set_target_device(b2icp_handle* h, const float* d_xyzw, size_t n);
+int b2icp_set_source_device(b2icp_handle* h, const float* d_xyzw, size_t n);
+/* `*prev_cloud_ = *curr_cloud_;` (icp_odometer.cpp:209): the current source becomes the target,
+ * keeping its device buffers (and, in GICP mode, its covariances). */
+int b2icp_promote_source_to_target(b2icp_handle* h);
+
+/* icp.align(out) + getFinalTransformation() + hasConverged()
+ * (icp_odometer.cpp:198-201, octree_mapper.cpp:114-117).  guess: 16 floats row-major or NULL
+ * (identity — the reference never passes one).  aligned_xyzw: n_source points or NULL. */
+int b2icp_align(b2icp_handle* h, const float* guess, b2icp_result* out, float* aligned_xyzw);
+
+/* icp.getFitnessScore(max_range) (icp_odometer.cpp:201; PCL default max_range = DBL_MAX):
+ * mean squared distance from every aligned source point to its exact nearest target point,
+ * counting only pairs with d^2 <= max_range.  Requires a completed b2icp_align. */
+int b2icp_fitness(b2icp_handle* h, double max_range, double* out);
+
+/* Correspondences of the last executed iteration: tgt_idx[i] = index into the target cloud as
+ * passed to b2icp_set_target, or -1 if gated out; sqdist[i] = float32 squared distance
+ * (undefined where idx = -1).  Either pointer may be NULL. */
+int b2icp_get_correspondences(b2icp_handle* h, int32_t* tgt_idx, float* sqdist);
+
+/* Stand-alone exact 1-NN of n query points against the current target (KdTreeFLANN::
+ * nearestKSearch(k=1), unbounded radius).  Ties in float32 d^2 resolve to the SMALLEST target
+ * index (canonical rule).  This is the roofline kernel. */
+int b2icp_nn_search(b2icp_handle* h, const float* q_xyzw, size_t n, int32_t* idx, float* sqdist);
+int b2icp_nn_search_device(b2icp_handle* h, const float* d_q_xyzw, size_t n, int32_t* d_idx,
+                           float* d_sqdist);
+
+/* pcl::transformPointCloud(in, out, Matrix4d) (icp_odometer.cpp:205): double math, float store. */
+int b2icp_transform_cloud(b2icp_handle* h, const float* in_xyzw, size_t n, const double* T,
+                          float* out_xyzw);
+/* pcl_ros::transformPointCloud(in, out, tf::Transform) (octree_mapper.cpp:96) after its
+ * conversion to Eigen::Matrix4f: float math. */
+int b2icp_transform_cloud_f(b2icp_handle* h, const float* in_xyzw, size_t n, const float* T,
+                            float* out_xyzw);
+
+/* Offline replay: `batch` independent (source, target) pairs, each what one laserCloudCallback
+ * does at icp_odometer.cpp:188-201.  If tgt[i] == NULL, pair i uses src[i-1] as its target
+ * (consecutive-sweep odometry; the uploaded cloud and its grid are reused on device). */
+int b2icp_align_batch(b2icp_handle* h, const float* const* src, const size_t* n_src,
+                      const float* const* tgt, const size_t* n_tgt, size_t batch,
+                      int with_fitness, b2icp_result* out);
+
+int b2icp_get_timing(b2icp_handle* h, b2icp_timing* out);
+const char* b2icp_last_error(const b2icp_handle* h);
+const char* b2icp_status_string(int status);
+int b2icp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2ICP_H_ */
