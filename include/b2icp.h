@@ -165,11 +165,21 @@ int b2icp_align_batch(b2icp_handle* h, const float* const* src, const size_t* n_
                       int with_fitness, b2icp_result* out);
 
 int b2icp_get_timing(b2icp_handle* h, b2icp_timing* out);
+/* Neighbour grid of the current target (the structure that replaces the FLANN k-d tree): cell edge,
+ * dims3 = {nx, ny, nz}, mean points per occupied cell.  Any pointer may be NULL. */
+int b2icp_get_grid_info(b2icp_handle* h, float* cell, int32_t* dims3, double* occupancy);
+/* Page-locked host buffers: clouds handed to the set / search calls from such memory are copied
+ * with true asynchronous DMA (pcl::PointCloud's allocator can be pointed here). */
+int b2icp_host_alloc(size_t bytes, void** out);
+int b2icp_host_free(void* p);
 const char* b2icp_last_error(const b2icp_handle* h);
 const char* b2icp_status_string(int status);
 int b2icp_version(void);
 
 #ifdef __cplusplus
 }
+static_assert(sizeof(b2icp_params) == 88, "b2icp_params layout is part of the ABI");
+static_assert(sizeof(b2icp_result) == 160, "b2icp_result layout is part of the ABI");
+static_assert(sizeof(b2icp_timing) == 48, "b2icp_timing layout is part of the ABI");
 #endif
 #endif /* B2ICP_H_ */

@@ -1,0 +1,262 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (include/b2icp.h), against the CPU oracle
+on the same seeded inputs.  Bars (BASELINE.json north_star):
+  * integer / index work (nearest-neighbour indices, correspondence indices): bit-exact;
+  * float32 squared distances and transformed points: bit-exact (same op order, no FMA);
+  * final transform per scan: 1e-4 m translation, 1e-4 rad rotation.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from icpslam_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+TOL_T = 1e-4    # metres      (north_star)
+TOL_R = 1e-4    # radians     (north_star)
+
+
+def rot_angle(Ra, Rb):
+    """Angle of Ra^T Rb from its skew part (well conditioned near 0, unlike acos of the trace)."""
+    R = Ra.T @ Rb
+    v = 0.5 * np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+    return math.asin(min(1.0, float(np.linalg.norm(v))))
+
+
+def assert_transform_close(Ta, Tb):
+    assert np.abs(Ta[:3, 3] - Tb[:3, 3]).max() <= TOL_T, (Ta[:3, 3], Tb[:3, 3])
+    assert rot_angle(Ta[:3, :3], Tb[:3, :3]) <= TOL_R
+
+
+@pytest.fixture(scope="module")
+def R(b2lib):
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return b2lib
+
+
+# ------------------------------------------------------------------------------------------------
+# K1 + K2: grid build + exact NN, bit-identical indices on integer fixtures
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_t,n_q", [(4096, 4096), (65536, 65536), (500000, 65536)])
+def test_nn_integer_fixture_bit_exact(R, oracle, n_t, n_q):
+    tgt = synth.integer_cloud(11 + n_t, n_t)
+    q = synth.integer_cloud(12 + n_q, n_q, unique=False)
+    reg = R.Registration(max_correspondence_distance=1e9)
+    reg.setInputTarget(tgt)
+    idx, d2 = reg.nearestKSearch1(q)
+    oi, od = oracle.KdTree(tgt).nn(q)
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(d2, od)
+    if n_t <= 65536:  # exhaustive scan as the second witness
+        bi, bd = oracle.nn_brute(tgt, q[:8192])
+        assert np.array_equal(idx[:8192], bi) and np.array_equal(d2[:8192], bd)
+
+
+def test_nn_tie_heavy_lattice_smallest_index_wins(R, oracle):
+    tgt = synth.integer_cloud(3, 3000, -8, 8)
+    q = synth.integer_cloud(4, 20000, -10, 10, unique=False)
+    reg = R.Registration(max_correspondence_distance=1e9)
+    reg.setInputTarget(tgt)
+    idx, d2 = reg.nearestKSearch1(q)
+    bi, bd = oracle.nn_brute(tgt, q)
+    assert np.array_equal(idx, bi) and np.array_equal(d2, bd)
+    # duplicates in the target (the mapper's NN cloud has them): still the smallest index
+    tgt2 = np.concatenate([tgt, tgt[:500]])
+    reg.setInputTarget(tgt2)
+    idx, d2 = reg.nearestKSearch1(q)
+    bi, bd = oracle.nn_brute(tgt2, q)
+    assert np.array_equal(idx, bi) and np.array_equal(d2, bd)
+
+
+def test_nn_real_valued_sweep_vs_oracle(R, oracle):
+    _, _, sw = synth.sweep_sequence(1, 2)
+    reg = R.Registration()
+    reg.setInputTarget(sw[0])
+    idx, d2 = reg.nearestKSearch1(sw[1])
+    oi, od = oracle.KdTree(sw[0]).nn(sw[1])
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(d2, od)
+
+
+def test_nn_far_queries_fall_back_to_exhaustive_scan(R, oracle):
+    rng = np.random.default_rng(5)
+    tgt = synth.as_xyzw(rng.uniform(-5, 5, (20000, 3)))
+    q = synth.as_xyzw(np.concatenate([rng.uniform(-5, 5, (1000, 3)), rng.uniform(200, 900, (300, 3)),
+                                      rng.uniform(-1e4, -5e3, (50, 3))]))
+    reg = R.Registration()
+    reg.setInputTarget(tgt)
+    idx, d2 = reg.nearestKSearch1(q)
+    bi, bd = oracle.nn_brute(tgt, q)
+    assert np.array_equal(idx, bi) and np.array_equal(d2, bd)
+
+
+def test_nn_planar_and_tiny_clouds(R, oracle):
+    _, _, scans = synth.planar_stream(3, 2)
+    reg = R.Registration()
+    reg.setInputTarget(scans[0])
+    idx, d2 = reg.nearestKSearch1(scans[1])
+    bi, bd = oracle.nn_brute(scans[0], scans[1])
+    assert np.array_equal(idx, bi) and np.array_equal(d2, bd)
+    one = synth.as_xyzw(np.array([[1.0, 2.0, 3.0]]))
+    reg.setInputTarget(one)
+    idx, d2 = reg.nearestKSearch1(scans[1][:10])
+    assert (idx == 0).all()
+    idx, d2 = reg.nearestKSearch1(scans[1][:0])
+    assert len(idx) == 0
+
+
+# ------------------------------------------------------------------------------------------------
+# K6: transforms, bit-exact float results
+# ------------------------------------------------------------------------------------------------
+def test_transform_cloud_bit_exact(R, oracle):
+    rng = np.random.default_rng(7)
+    cloud = synth.as_xyzw(rng.uniform(-80, 80, (10001, 3)))
+    T = synth.random_rigid(rng, 3.0, 0.7)
+    reg = R.Registration()
+    assert np.array_equal(reg.transformPointCloud(cloud, T, double=True), oracle.transform_cloud(cloud, T, True))
+    assert np.array_equal(reg.transformPointCloud(cloud, T, double=False), oracle.transform_cloud(cloud, T, False))
+
+
+# ------------------------------------------------------------------------------------------------
+# full ICP loop (point-to-point, north_star pipeline)
+# ------------------------------------------------------------------------------------------------
+def run_pair(R, oracle, src, tgt, preset, **over):
+    reg = R.Registration(preset=preset, **over)
+    reg.setInputSource(src)
+    reg.setInputTarget(tgt)
+    aligned = reg.align(want_aligned=True)
+    p = oracle.default_params("odometer" if preset == R.PRESET_ODOMETER else "mapper")
+    for k, v in over.items():
+        setattr(p, k, v)
+    o = oracle.align(p, src, tgt, want_aligned=True, record_iter=-1)
+    return reg, aligned, o
+
+
+def test_config1_4k_scan_pair_10_iterations(R, oracle):
+    """BASELINE.json configs[0]: single 4k-pt scan vs 4k-pt previous scan, 10 ICP iterations."""
+    _, _, sw = synth.sweep_sequence(1, 2, n_beams=64, n_az=64)
+    assert sw[0].shape == (4096, 4)
+    reg, aligned, o = run_pair(R, oracle, sw[1], sw[0], R.PRESET_ODOMETER)
+    assert o["rc"] == 0
+    assert reg.iterations == o["iterations"]
+    assert reg.hasConverged() == bool(o["converged"])
+    assert_transform_close(reg.getFinalTransformation(), o["T"])
+    idx, d2 = reg.getCorrespondences()
+    assert np.array_equal(idx, o["corr_idx"])          # bit-identical correspondence indices
+    keep = idx >= 0
+    assert np.array_equal(d2[keep], o["corr_d2"][keep])
+    assert reg.result.n_corr_last == o["n_corr"]
+    assert abs(reg.result.mse_last - o["mse"]) <= 1e-9
+    assert np.abs(aligned - o["aligned"]).max() <= 2e-5
+    fit = reg.getFitnessScore()
+    ofit = oracle.fitness(sw[1], sw[0], reg.getFinalTransformation().astype(np.float32))
+    assert abs(fit - ofit) <= 1e-9 * max(1.0, ofit)
+
+
+def test_config4_unit_64k_scan_pair_30_iterations(R, oracle):
+    """One work item of BASELINE.json configs[3]: consecutive 64k-pt sweeps, 30 iterations."""
+    _, _, sw = synth.sweep_sequence(4, 2)
+    reg, aligned, o = run_pair(R, oracle, sw[1], sw[0], R.PRESET_MAPPER)
+    assert reg.iterations == o["iterations"]
+    assert_transform_close(reg.getFinalTransformation(), o["T"])
+    idx, _ = reg.getCorrespondences()
+    assert np.array_equal(idx, o["corr_idx"])
+
+
+def test_config3_planar_1080pt_scan_to_scan(R, oracle):
+    """BASELINE.json configs[2]: 2-D planar 1080-pt scans (z = 0: rank-2 covariance, nz = 1 grid)."""
+    _, _, scans = synth.planar_stream(3, 6)
+    for i in range(1, 6):
+        reg, _, o = run_pair(R, oracle, scans[i], scans[i - 1], R.PRESET_ODOMETER)
+        assert reg.iterations == o["iterations"]
+        assert_transform_close(reg.getFinalTransformation(), o["T"])
+        T = reg.getFinalTransformation()
+        assert abs(T[2, 3]) < 1e-6 and abs(T[2, 2] - 1) < 1e-6
+
+
+def test_analytic_kat_exact_rigid_motion(R):
+    """Q = T*P, same order, no noise: ICP must return T (SURVEY.md §4 KATs)."""
+    rng = np.random.default_rng(0)
+    P = synth.as_xyzw(rng.uniform(-5, 5, (5000, 3)))
+    T = synth.random_rigid(rng, 0.05, 0.01)
+    Q = synth.as_xyzw((P[:, :3].astype(np.float64) @ T[:3, :3].T + T[:3, 3]))
+    reg = R.Registration(preset=R.PRESET_MAPPER)
+    reg.setInputSource(P)
+    reg.setInputTarget(Q)
+    reg.align()
+    assert reg.hasConverged()
+    assert np.abs(reg.getFinalTransformation() - T).max() < 5e-6
+    # identity
+    reg.setInputTarget(P)
+    reg.align()
+    assert np.abs(reg.getFinalTransformation() - np.eye(4)).max() < 1e-6
+    assert reg.iterations <= 2
+
+
+def test_guess_is_applied_like_pcl(R, oracle):
+    _, _, sw = synth.sweep_sequence(1, 2, n_beams=64, n_az=64)
+    g = synth.random_rigid(np.random.default_rng(3), 0.1, 0.01).astype(np.float32)
+    reg = R.Registration()
+    reg.setInputSource(sw[1])
+    reg.setInputTarget(sw[0])
+    reg.align(guess=g)
+    o = oracle.align(oracle.default_params("odometer"), sw[1], sw[0], guess=g)
+    assert reg.iterations == o["iterations"]
+    assert_transform_close(reg.getFinalTransformation(), o["T"])
+
+
+def test_promote_source_to_target_is_prev_equals_curr(R, oracle):
+    """`*prev_cloud_ = *curr_cloud_` (reference icp_odometer.cpp:209) on device, then the next pair."""
+    _, _, sw = synth.sweep_sequence(2, 3, n_beams=64, n_az=128)
+    reg = R.Registration()
+    reg.setInputTarget(sw[0])
+    reg.setInputSource(sw[1])
+    reg.align()
+    reg.promoteSourceToTarget()
+    reg.setInputSource(sw[2])
+    reg.align()
+    o = oracle.align(oracle.default_params("odometer"), sw[2], sw[1])
+    assert reg.iterations == o["iterations"]
+    assert_transform_close(reg.getFinalTransformation(), o["T"])
+    rc, res = reg.alignBatch([sw[1], sw[2]], [sw[0], None], with_fitness=True)
+    assert rc == 0
+    assert_transform_close(res[1].matrix(), o["T"])
+    assert res[1].fitness < 20  # the reference's acceptance test (icp_odometer.cpp:201)
+
+
+def test_error_codes(R):
+    reg = R.Registration()
+    cloud = synth.as_xyzw(np.random.default_rng(1).uniform(-1, 1, (100, 3)))
+    with pytest.raises(R.B2icpError) as e:
+        reg.align()
+    assert e.value.code == -9  # NO_SOURCE
+    reg.setInputSource(cloud)
+    with pytest.raises(R.B2icpError) as e:
+        reg.align()
+    assert e.value.code == -8  # NO_TARGET
+    with pytest.raises(R.B2icpError) as e:
+        reg.setInputTarget(cloud[:0])
+    assert e.value.code == -2  # EMPTY_CLOUD
+    bad = cloud.copy()
+    bad[3, 1] = np.nan
+    with pytest.raises(R.B2icpError) as e:
+        reg.setInputTarget(bad)
+    assert e.value.code == -6  # NONFINITE_INPUT
+    reg.setInputTarget(cloud)
+    reg.setInputSource(bad)
+    with pytest.raises(R.B2icpError) as e:
+        reg.align()
+    assert e.value.code == -6
+    # far-apart clouds: fewer than 3 correspondences inside 1 m -> PCL leaves converged_ = false
+    far = cloud.copy()
+    far[:, :3] += 50
+    reg.setInputSource(far)
+    with pytest.raises(R.B2icpError) as e:
+        reg.align()
+    assert e.value.code == -4
+    assert not reg.hasConverged()
+    with pytest.raises(R.B2icpError) as e:
+        R.Registration().getFitnessScore()
+    assert e.value.code == -10
