@@ -3,14 +3,22 @@
 // Drop-in boundary for the PCL registration object the reference builds on the stack
 // (reference src/icpslam/icp_odometer.cpp:188-201, src/icpslam/octree_mapper.cpp:104-117).
 // No C++ exception crosses this file's extern "C" functions; there is no CPU fallback.
+//
+// Execution model: a handle owns one CUDA stream, a pool of SCAN SLOTS (source cloud + running cloud
+// + correspondence buffers + per-CTA partial sums) and a pool of GRID SLOTS (target cloud + its
+// neighbour grid).  The single-scan entry points use slot 0 / grid 0; b2icp_align_batch fills up to
+// kMaxBatch slots and advances all of them with ONE launch of the fused sweep kernel per ICP
+// iteration (blockIdx.y = slot), so that a 148-SM part is filled by independent scans.
 #include "../../include/b2icp.h"
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <string>
@@ -30,6 +38,7 @@ constexpr int kMaxCells = 1 << 25;        // dense cell table cap (128 MiB of in
 constexpr int kUnboundedRings = 3;        // ring budget of unbounded searches before the brute-force fallback
 constexpr double kTargetOccupancy = 6.0;  // points per occupied cell the auto-sizing aims at
 constexpr double kMaxOccupancy = 24.0;    // above this the grid is rebuilt with smaller cells
+constexpr int kMaxBatch = 64;             // scans advanced together by one sweep launch
 
 struct DeviceBuf {
   void* p = nullptr;
@@ -61,39 +70,28 @@ struct Cloud {
   bool valid = false;
 };
 
-struct Grid {
-  DeviceBuf sorted, cell_start, cell_of, rank;
+struct GridSlot {
+  Cloud tgt;                     // owned copy of the target (unused when the grid borrows a slot's source)
+  const float4* pts = nullptr;   // the cloud the grid indexes
+  DeviceBuf sorted, cell_start, cell_of, rank, tile_sums, bbox;
   GridView view;
-  double occupancy = 0;  // mean points per occupied cell
+  double cell = 0, min_cell = 0;
+  float mn[3], mx[3];
+  double occupancy = 0;
   bool valid = false;
-};
-
-struct SetupArgs {
-  ScanTask task;
-  float guess[16];
-};
-
-__global__ void icp_setup_kernel(ScanTask* tasks, IcpState* st, SetupArgs a) {
-  if (threadIdx.x == 0) {
-    tasks[0] = a.task;
-    for (int i = 0; i < 16; ++i) {
-      st->Tinc[i] = a.guess[i];
-      st->final_T[i] = a.guess[i];
-    }
-    st->mse = nan("");
-    st->prev_mse = DBL_MAX;
-    st->fitness_sum = 0;
-    st->fitness_cnt = 0;
-    st->iter = 0;
-    st->done = 0;
-    st->converged = 0;
-    st->status = 0;
-    st->n_corr = 0;
-    st->ticket = 0;
-    st->unresolved = 0;
-    st->pad = 0;
+  void release() {
+    for (DeviceBuf* b : {&tgt.raw, &sorted, &cell_start, &cell_of, &rank, &tile_sums, &bbox}) b->release();
   }
-}
+};
+
+struct ScanSlot {
+  Cloud src;
+  DeviceBuf cur, corr_idx, corr_d2, corr_pos, partials;
+  int grid = 0;
+  void release() {
+    for (DeviceBuf* b : {&src.raw, &cur, &corr_idx, &corr_d2, &corr_pos, &partials}) b->release();
+  }
+};
 
 __global__ void zero_counter(unsigned int* c) { *c = 0; }
 
@@ -104,19 +102,23 @@ struct b2icp_handle {
   IcpConfig cfg;
   int device = 0;
   cudaStream_t stream = nullptr;
+  bool own_stream = true;
   std::mutex mu;
   std::string err;
 
-  Cloud src, tgt;
-  Grid grid;
-  DeviceBuf cur, corr_idx, corr_d2, partials, state, tasks, bbox, tile_sums, unres_list, unres_count;
+  std::vector<std::unique_ptr<ScanSlot>> slots;
+  std::vector<std::unique_ptr<GridSlot>> grids;
+  DeviceBuf states, tasks, unres_list, unres_count;
   DeviceBuf query, q_idx, q_d2, xf_in, xf_out, mat;
-  IcpState* h_state = nullptr;  // pinned
-  BBox* h_bbox = nullptr;       // pinned
-  bool aligned = false;
+  IcpState* h_states = nullptr;  // pinned [kMaxBatch]: upload (init) and read-back
+  ScanTask* h_tasks = nullptr;   // pinned [kMaxBatch]
+  BBox* h_bbox = nullptr;        // pinned [kMaxBatch + 1]
+  bool aligned = false;          // slot 0 holds a completed align
+  int last_batch = 0;
 
   std::vector<cudaEvent_t> events;
   b2icp_timing timing;
+  long long launches = 0;
 };
 
 namespace {
@@ -133,6 +135,15 @@ namespace {
 int fail(b2icp_handle* h, int code, const char* msg) {
   if (h) h->err = msg;
   return code;
+}
+
+ScanSlot& slot(b2icp_handle* h, size_t i) {
+  while (h->slots.size() <= i) h->slots.emplace_back(new ScanSlot());
+  return *h->slots[i];
+}
+GridSlot& gslot(b2icp_handle* h, size_t i) {
+  while (h->grids.size() <= i) h->grids.emplace_back(new GridSlot());
+  return *h->grids[i];
 }
 
 void derive_config(b2icp_handle* h) {
@@ -152,100 +163,135 @@ void derive_config(b2icp_handle* h) {
   c.max_rings = 1;
 }
 
-int rings_for_bound(const b2icp_handle* h) {
-  if (!h->grid.valid || !std::isfinite(h->cfg.bound2)) return kUnboundedRings;
+int rings_for_bound(const b2icp_handle* h, double min_cell) {
+  if (!std::isfinite(h->cfg.bound2)) return kUnboundedRings;
   double r = std::sqrt((double)h->cfg.bound2);
-  double k = std::ceil(r / (double)h->grid.view.cell) + 2.0;
+  double k = std::ceil(r / min_cell) + 2.0;
   return k > 1e6 ? 1000000 : (int)k;
 }
 
-// K1: build the neighbour grid over h->tgt.raw
-int build_grid(b2icp_handle* h) {
-  const int n = (int)h->tgt.n;
-  const float4* pts = h->tgt.raw.as<float4>();
-  const int blocks = (n + 255) / 256;
-  bbox_init<<<1, 32, 0, h->stream>>>(h->bbox.as<BBox>());
-  bbox_kernel<<<std::min(blocks, 148 * 8), 256, 0, h->stream>>>(pts, n, h->bbox.as<BBox>());
-  CK(cudaMemcpyAsync(h->h_bbox, h->bbox.p, sizeof(BBox), cudaMemcpyDeviceToHost, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  if (h->h_bbox->nonfinite) return fail(h, B2ICP_ERR_NONFINITE_INPUT, "target cloud holds non-finite coordinates");
-  float mn[3], mx[3];
-  double ext[3];
-  for (int d = 0; d < 3; ++d) {
-    mn[d] = ord2f(h->h_bbox->mn[d]);
-    mx[d] = ord2f(h->h_bbox->mx[d]);
-    ext[d] = (double)mx[d] - (double)mn[d];
+// ---- K1: neighbour-grid build, split in phases so that a batch needs two host syncs in total ------
+// phase A: bounding boxes of `count` clouds -> h->h_bbox[0..count)
+int grids_bbox(b2icp_handle* h, GridSlot* const* g, const size_t* n, int count) {
+  for (int i = 0; i < count; ++i) {
+    CK(g[i]->bbox.ensure(sizeof(BBox)));
+    const int blocks = (int)((n[i] + 255) / 256);
+    bbox_init<<<1, 32, 0, h->stream>>>(g[i]->bbox.as<BBox>());
+    bbox_kernel<<<std::min(blocks, 148 * 8), 256, 0, h->stream>>>(g[i]->pts, (int)n[i], g[i]->bbox.as<BBox>());
+    h->launches += 2;
+    CK(cudaMemcpyAsync(&h->h_bbox[i], g[i]->bbox.p, sizeof(BBox), cudaMemcpyDeviceToHost, h->stream));
   }
-  const double emax = std::max(ext[0], std::max(ext[1], ext[2]));
-  // density-based cell: ~kTargetOccupancy points per cell if the cloud filled its box uniformly;
-  // axes thinner than 1e-6 of the largest extent (planar scans) are left out of the estimate
-  double vol = 1.0;
-  int dims = 0;
-  for (int d = 0; d < 3; ++d)
-    if (ext[d] > 1e-6 * emax && ext[d] > 0) {
-      vol *= ext[d];
-      ++dims;
+  CK(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < count; ++i) {
+    if (h->h_bbox[i].nonfinite) return fail(h, B2ICP_ERR_NONFINITE_INPUT, "target cloud holds non-finite coordinates");
+    double ext[3];
+    for (int d = 0; d < 3; ++d) {
+      g[i]->mn[d] = ord2f(h->h_bbox[i].mn[d]);
+      g[i]->mx[d] = ord2f(h->h_bbox[i].mx[d]);
+      ext[d] = (double)g[i]->mx[d] - (double)g[i]->mn[d];
     }
-  double cell = 1.0;
-  if (dims > 0) cell = std::pow(vol * kTargetOccupancy / (double)n, 1.0 / dims);
-  const double r = h->params.max_correspondence_distance;
-  if (r > 0 && std::isfinite(r)) cell = std::min(cell, 0.5 * r);
-  if (h->params.grid_cell > 0) cell = h->params.grid_cell;
-  if (!(cell > 0) || !std::isfinite(cell)) cell = 1.0;
-  const double min_cell = (h->params.grid_cell > 0) ? cell : ((r > 0 && std::isfinite(r)) ? std::min(cell, r / 8.0) : cell / 8.0);
+    const double emax = std::max(ext[0], std::max(ext[1], ext[2]));
+    // density-based cell: ~kTargetOccupancy points per cell if the cloud filled its box uniformly;
+    // axes thinner than 1e-6 of the largest extent (planar scans) are left out of the estimate
+    double vol = 1.0;
+    int dims = 0;
+    for (int d = 0; d < 3; ++d)
+      if (ext[d] > 1e-6 * emax && ext[d] > 0) {
+        vol *= ext[d];
+        ++dims;
+      }
+    double cell = 1.0;
+    if (dims > 0) cell = std::pow(vol * kTargetOccupancy / (double)n[i], 1.0 / dims);
+    const double r = h->params.max_correspondence_distance;
+    const bool bounded = r > 0 && std::isfinite(r) && r < 1e8;
+    if (bounded) cell = std::min(cell, 0.5 * r);
+    if (h->params.grid_cell > 0) cell = h->params.grid_cell;
+    if (!(cell > 0) || !std::isfinite(cell)) cell = 1.0;
+    g[i]->cell = cell;
+    g[i]->min_cell = (h->params.grid_cell > 0) ? cell : (bounded ? std::min(cell, r / 8.0) : cell / 8.0);
+  }
+  return B2ICP_OK;
+}
 
-  for (int attempt = 0; attempt < 3; ++attempt) {
-    // respect the dense-table cap
-    long long nx, ny, nz;
-    for (;;) {
-      nx = (long long)std::floor(ext[0] / cell) + 1;
-      ny = (long long)std::floor(ext[1] / cell) + 1;
-      nz = (long long)std::floor(ext[2] / cell) + 1;
-      if ((double)nx * (double)ny * (double)nz <= (double)kMaxCells) break;
-      cell *= 1.26;
+// phase B: enqueue the counting sort of one cloud with the cell size chosen in g->cell
+int grid_enqueue_build(b2icp_handle* h, GridSlot* g, size_t n_) {
+  const int n = (int)n_;
+  double ext[3];
+  for (int d = 0; d < 3; ++d) ext[d] = (double)g->mx[d] - (double)g->mn[d];
+  const double emax = std::max(ext[0], std::max(ext[1], ext[2]));
+  long long nx, ny, nz;
+  for (;;) {  // respect the dense-table cap
+    nx = (long long)std::floor(ext[0] / g->cell) + 1;
+    ny = (long long)std::floor(ext[1] / g->cell) + 1;
+    nz = (long long)std::floor(ext[2] / g->cell) + 1;
+    if ((double)nx * (double)ny * (double)nz <= (double)kMaxCells) break;
+    g->cell *= 1.26;
+  }
+  GridView& v = g->view;
+  v.ox = g->mn[0];
+  v.oy = g->mn[1];
+  v.oz = g->mn[2];
+  v.cell = (float)g->cell;
+  v.inv_cell = 1.0f / v.cell;
+  v.nx = (int)nx;
+  v.ny = (int)ny;
+  v.nz = (int)nz;
+  v.n = n;
+  float amax = 0.f;
+  for (int d = 0; d < 3; ++d) amax = std::max(amax, std::max(std::fabs(g->mn[d]), std::fabs(g->mx[d]) + v.cell));
+  v.slack = std::max(amax, (float)emax) * 9.5367431640625e-7f + 1e-30f;  // 2^-20 of the coordinate range
+  const int ncell = v.nx * v.ny * v.nz;
+  CK(g->cell_start.ensure((size_t)(ncell + 1 + 4) * sizeof(int)));
+  CK(g->sorted.ensure((size_t)n * sizeof(float4)));
+  CK(g->cell_of.ensure((size_t)n * sizeof(int)));
+  CK(g->rank.ensure((size_t)n * sizeof(int)));
+  const int ntiles = (ncell + kScanTile - 1) / kScanTile;
+  CK(g->tile_sums.ensure((size_t)ntiles * sizeof(int)));
+  int* cs = g->cell_start.as<int>();
+  const int blocks = (n + 255) / 256;
+  CK(cudaMemsetAsync(cs, 0, (size_t)(ncell + 1) * sizeof(int), h->stream));
+  bbox_init<<<1, 32, 0, h->stream>>>(g->bbox.as<BBox>());
+  grid_count<<<blocks, 256, 0, h->stream>>>(g->pts, n, v, g->cell_of.as<int>(), g->rank.as<int>(), cs);
+  scan_tile_sums<<<ntiles, kScanThreads, 0, h->stream>>>(cs, ncell, g->tile_sums.as<int>(), g->bbox.as<BBox>());
+  scan_of_sums<<<1, kScanThreads, 0, h->stream>>>(g->tile_sums.as<int>(), ntiles);
+  scan_apply<<<ntiles, kScanThreads, 0, h->stream>>>(cs, ncell, g->tile_sums.as<int>(), n);
+  grid_scatter<<<blocks, 256, 0, h->stream>>>(g->pts, n, g->cell_of.as<int>(), g->rank.as<int>(), cs,
+                                               g->sorted.as<float4>());
+  h->launches += 6;
+  v.pts = g->sorted.as<float4>();
+  v.cell_start = cs;
+  return B2ICP_OK;
+}
+
+// Build `count` grids (bbox pass, sort, occupancy check with at most two refinements).
+int build_grids(b2icp_handle* h, GridSlot* const* g, const size_t* n, int count) {
+  for (int i = 0; i < count; ++i) g[i]->valid = false;
+  int rc = grids_bbox(h, g, n, count);
+  if (rc) return rc;
+  std::vector<int> todo(count);
+  for (int i = 0; i < count; ++i) todo[i] = i;
+  for (int attempt = 0; attempt < 3 && !todo.empty(); ++attempt) {
+    for (int i : todo) {
+      rc = grid_enqueue_build(h, g[i], n[i]);
+      if (rc) return rc;
+      CK(cudaMemcpyAsync(&h->h_bbox[i], g[i]->bbox.p, sizeof(BBox), cudaMemcpyDeviceToHost, h->stream));
     }
-    GridView& g = h->grid.view;
-    g.ox = mn[0];
-    g.oy = mn[1];
-    g.oz = mn[2];
-    g.cell = (float)cell;
-    g.inv_cell = 1.0f / g.cell;
-    g.nx = (int)nx;
-    g.ny = (int)ny;
-    g.nz = (int)nz;
-    g.n = n;
-    float amax = 0.f;
-    for (int d = 0; d < 3; ++d) amax = std::max(amax, std::max(std::fabs(mn[d]), std::fabs(mx[d]) + g.cell));
-    g.slack = std::max(amax, (float)emax) * 9.5367431640625e-7f + 1e-30f;  // 2^-20 relative
-    const int ncell = g.nx * g.ny * g.nz;
-    CK(h->grid.cell_start.ensure((size_t)(ncell + 1 + 4) * sizeof(int)));
-    CK(h->grid.sorted.ensure((size_t)n * sizeof(float4)));
-    CK(h->grid.cell_of.ensure((size_t)n * sizeof(int)));
-    CK(h->grid.rank.ensure((size_t)n * sizeof(int)));
-    const int ntiles = (ncell + kScanTile - 1) / kScanTile;
-    CK(h->tile_sums.ensure((size_t)ntiles * sizeof(int)));
-    int* cs = h->grid.cell_start.as<int>();
-    CK(cudaMemsetAsync(cs, 0, (size_t)(ncell + 1) * sizeof(int), h->stream));
-    bbox_init<<<1, 32, 0, h->stream>>>(h->bbox.as<BBox>());
-    grid_count<<<blocks, 256, 0, h->stream>>>(pts, n, g, h->grid.cell_of.as<int>(), h->grid.rank.as<int>(), cs);
-    scan_tile_sums<<<ntiles, kScanThreads, 0, h->stream>>>(cs, ncell, h->tile_sums.as<int>(), h->bbox.as<BBox>());
-    scan_of_sums<<<1, kScanThreads, 0, h->stream>>>(h->tile_sums.as<int>(), ntiles);
-    scan_apply<<<ntiles, kScanThreads, 0, h->stream>>>(cs, ncell, h->tile_sums.as<int>(), n);
-    grid_scatter<<<blocks, 256, 0, h->stream>>>(pts, n, h->grid.cell_of.as<int>(), h->grid.rank.as<int>(), cs,
-                                                 h->grid.sorted.as<float4>());
-    CK(cudaMemcpyAsync(h->h_bbox, h->bbox.p, sizeof(BBox), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());
-    g.pts = h->grid.sorted.as<float4>();
-    g.cell_start = cs;
-    const int occ_cells = std::max(1, h->h_bbox->occupied);
-    h->grid.occupancy = (double)n / (double)occ_cells;
-    if (h->grid.occupancy <= kMaxOccupancy || cell <= min_cell * 1.0001) break;
-    // surfaces: occupancy scales ~ cell^2
-    double shrink = std::sqrt(kTargetOccupancy / h->grid.occupancy);
-    cell = std::max(min_cell, cell * std::max(shrink, 0.25));
+    std::vector<int> again;
+    for (int i : todo) {
+      const int occ_cells = std::max(1, h->h_bbox[i].occupied);
+      g[i]->occupancy = (double)n[i] / (double)occ_cells;
+      if (g[i]->occupancy > kMaxOccupancy && g[i]->cell > g[i]->min_cell * 1.0001) {
+        // surfaces: occupancy scales ~ cell^2
+        double shrink = std::sqrt(kTargetOccupancy / g[i]->occupancy);
+        g[i]->cell = std::max(g[i]->min_cell, g[i]->cell * std::max(shrink, 0.25));
+        again.push_back(i);
+      }
+    }
+    todo.swap(again);
   }
-  h->grid.valid = true;
+  for (int i = 0; i < count; ++i) g[i]->valid = true;
   return B2ICP_OK;
 }
 
@@ -260,42 +306,29 @@ int upload_cloud(b2icp_handle* h, Cloud& c, const float* xyzw, size_t n, bool fr
   return B2ICP_OK;
 }
 
-int set_target_impl(b2icp_handle* h, const float* xyzw, size_t n, bool from_device) {
-  h->grid.valid = false;
-  h->tgt.valid = false;
-  h->aligned = false;
-  int rc = upload_cloud(h, h->tgt, xyzw, n, from_device);
+int set_target_impl(b2icp_handle* h, int gi, const float* xyzw, size_t n, bool from_device) {
+  GridSlot& g = gslot(h, gi);
+  g.valid = false;
+  g.tgt.valid = false;
+  if (gi == 0) h->aligned = false;
+  int rc = upload_cloud(h, g.tgt, xyzw, n, from_device);
   if (rc) return rc;
-  rc = build_grid(h);
-  if (rc) h->tgt.valid = false;
+  g.pts = g.tgt.raw.as<float4>();
+  GridSlot* gp = &g;
+  rc = build_grids(h, &gp, &n, 1);
+  if (rc) g.tgt.valid = false;
   return rc;
 }
 
-int set_source_impl(b2icp_handle* h, const float* xyzw, size_t n, bool from_device) {
-  h->src.valid = false;
-  h->aligned = false;
-  return upload_cloud(h, h->src, xyzw, n, from_device);
-}
-
-int ensure_work(b2icp_handle* h, size_t n) {
+int ensure_slot_work(b2icp_handle* h, ScanSlot& s) {
+  const size_t n = s.src.n;
   const size_t ncta = (n + kSweepThreads - 1) / kSweepThreads;
-  CK(h->cur.ensure(n * sizeof(float4)));
-  CK(h->corr_idx.ensure(n * sizeof(int)));
-  CK(h->corr_d2.ensure(n * sizeof(float)));
-  CK(h->partials.ensure(ncta * kNumSums * sizeof(double)));
-  CK(h->unres_list.ensure(n * sizeof(int)));
+  CK(s.cur.ensure(n * sizeof(float4)));
+  CK(s.corr_idx.ensure(n * sizeof(int)));
+  CK(s.corr_d2.ensure(n * sizeof(float)));
+  CK(s.corr_pos.ensure(n * sizeof(int)));
+  CK(s.partials.ensure(ncta * kNumSums * sizeof(double)));
   return B2ICP_OK;
-}
-
-void fill_result(const b2icp_handle* h, b2icp_result* out) {
-  const IcpState& s = *h->h_state;
-  for (int i = 0; i < 16; ++i) out->T[i] = (double)s.final_T[i];
-  out->converged = s.converged;
-  out->iterations = s.iter;
-  out->n_corr_last = s.n_corr;
-  out->status_detail = s.status;
-  out->mse_last = s.mse;
-  out->fitness = std::nan("");
 }
 
 void identity_result(b2icp_result* out) {
@@ -305,29 +338,53 @@ void identity_result(b2icp_result* out) {
   out->fitness = std::nan("");
 }
 
-int align_impl(b2icp_handle* h, const float* guess, b2icp_result* out, float* aligned_xyzw) {
-  if (!out) return fail(h, B2ICP_ERR_INVALID_ARG, "out == NULL");
-  identity_result(out);
-  if (!h->src.valid) return fail(h, B2ICP_ERR_NO_SOURCE, "no source cloud set");
-  if (!h->tgt.valid || !h->grid.valid) return fail(h, B2ICP_ERR_NO_TARGET, "no target cloud set");
-  if (h->params.mode != B2ICP_MODE_P2P_SVD) return fail(h, B2ICP_ERR_INVALID_ARG, "mode not implemented");
-  const size_t n = h->src.n;
-  int rc = ensure_work(h, n);
-  if (rc) return rc;
-  h->cfg.max_rings = rings_for_bound(h);
+void fill_result(const IcpState& s, b2icp_result* out) {
+  for (int i = 0; i < 16; ++i) out->T[i] = (double)s.final_T[i];
+  out->converged = s.converged;
+  out->iterations = s.iter;
+  out->n_corr_last = s.n_corr;
+  out->status_detail = s.status;
+  out->mse_last = s.mse;
+  out->fitness = std::nan("");
+}
 
-  SetupArgs a;
-  a.task.grid = h->grid.view;
-  a.task.src = h->src.raw.as<float4>();
-  a.task.cur = h->cur.as<float4>();
-  a.task.corr_idx = h->corr_idx.as<int>();
-  a.task.corr_d2 = h->corr_d2.as<float>();
-  a.task.partials = h->partials.as<double>();
-  a.task.state = h->state.as<IcpState>();
-  a.task.n = (int)n;
-  a.task.pad = 0;
-  for (int i = 0; i < 16; ++i) a.guess[i] = guess ? guess[i] : ((i % 5 == 0) ? 1.f : 0.f);
-  icp_setup_kernel<<<1, 32, 0, h->stream>>>(h->tasks.as<ScanTask>(), h->state.as<IcpState>(), a);
+// Advance slots [0, B) to convergence: one fused sweep launch per iteration for the whole batch.
+// guesses: B x 16 floats or NULL.  Results are read back by read_states().
+int run_batch(b2icp_handle* h, int B, const float* guesses) {
+  if (h->params.mode != B2ICP_MODE_P2P_SVD) return fail(h, B2ICP_ERR_INVALID_ARG, "mode not implemented");
+  size_t max_n = 0;
+  double min_cell = 1e300;
+  for (int i = 0; i < B; ++i) {
+    ScanSlot& s = slot(h, i);
+    GridSlot& g = gslot(h, s.grid);
+    int rc = ensure_slot_work(h, s);
+    if (rc) return rc;
+    max_n = std::max(max_n, s.src.n);
+    min_cell = std::min(min_cell, (double)g.view.cell);
+    ScanTask& t = h->h_tasks[i];
+    t.grid = g.view;
+    t.src = s.src.raw.as<float4>();
+    t.cur = s.cur.as<float4>();
+    t.corr_idx = s.corr_idx.as<int>();
+    t.corr_d2 = s.corr_d2.as<float>();
+    t.corr_pos = s.corr_pos.as<int>();
+    t.partials = s.partials.as<double>();
+    t.state = h->states.as<IcpState>() + i;
+    t.n = (int)s.src.n;
+    t.pad = 0;
+    IcpState& st = h->h_states[i];
+    std::memset(&st, 0, sizeof(st));
+    for (int k = 0; k < 16; ++k) {
+      const float v = guesses ? guesses[16 * i + k] : ((k % 5 == 0) ? 1.f : 0.f);
+      st.Tinc[k] = v;
+      st.final_T[k] = v;
+    }
+    st.mse = std::nan("");
+    st.prev_mse = DBL_MAX;
+  }
+  h->cfg.max_rings = rings_for_bound(h, min_cell);
+  CK(cudaMemcpyAsync(h->tasks.p, h->h_tasks, sizeof(ScanTask) * B, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->states.p, h->h_states, sizeof(IcpState) * B, cudaMemcpyHostToDevice, h->stream));
 
   const bool prof = h->params.profile != 0;
   const int iters = std::max(h->params.max_iterations, 1);
@@ -339,54 +396,171 @@ int align_impl(b2icp_handle* h, const float* guess, b2icp_result* out, float* al
     }
     CK(cudaEventRecord(h->events[0], h->stream));
   }
-  dim3 grid((unsigned)((n + kSweepThreads - 1) / kSweepThreads), 1, 1);
+  dim3 grid((unsigned)((max_n + kSweepThreads - 1) / kSweepThreads), (unsigned)B, 1);
   for (int it = 0; it < iters; ++it) {
     if (prof) CK(cudaEventRecord(h->events[2 + 2 * it], h->stream));
     icp_sweep_p2p<<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>(), h->cfg);
     if (prof) CK(cudaEventRecord(h->events[3 + 2 * it], h->stream));
   }
+  h->launches += iters;
   if (prof) CK(cudaEventRecord(h->events[1], h->stream));
-  if (aligned_xyzw) {
-    CK(h->xf_out.ensure(n * sizeof(float4)));
-    transform_cloud_f<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(
-        h->src.raw.as<float4>(), (int)n, h->state.as<IcpState>()->final_T, h->xf_out.as<float4>());
-    CK(cudaMemcpyAsync(aligned_xyzw, h->xf_out.p, n * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
-  }
-  CK(cudaMemcpyAsync(h->h_state, h->state.p, sizeof(IcpState), cudaMemcpyDeviceToHost, h->stream));
+  h->last_batch = B;
+  return B2ICP_OK;
+}
+
+int read_states(b2icp_handle* h, int B) {
+  CK(cudaMemcpyAsync(h->h_states, h->states.p, sizeof(IcpState) * B, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
-  fill_result(h, out);
-  h->aligned = true;
-  if (prof) {
+  if (h->params.profile != 0 && h->events.size() >= 2) {
     b2icp_timing& t = h->timing;
     std::memset(&t, 0, sizeof(t));
     float ms = 0;
     cudaEventElapsedTime(&ms, h->events[0], h->events[1]);
     t.total_ms = ms;
-    const int ran = std::min(iters, std::max(h->h_state->iter, 1));
+    int ran = 1;
+    for (int i = 0; i < B; ++i) ran = std::max(ran, h->h_states[i].iter);
+    ran = std::min(ran, std::max(h->params.max_iterations, 1));
     for (int it = 0; it < ran; ++it) {
       cudaEventElapsedTime(&ms, h->events[2 + 2 * it], h->events[3 + 2 * it]);
       t.nn_sweep_ms += ms;
     }
     t.nn_sweep_launches = ran;
   }
-  if (h->h_state->status != 0) {
-    h->err = h->h_state->status == B2ICP_ERR_NONFINITE_INPUT ? "non-finite source point or transform"
-                                                              : "ICP loop ended early: not enough correspondences";
-    return h->h_state->status;
-  }
+  h->timing.kernel_launches = h->launches;
   return B2ICP_OK;
 }
 
+const char* status_message(int s) {
+  switch (s) {
+    case B2ICP_ERR_NONFINITE_INPUT: return "non-finite source point or transform";
+    case B2ICP_ERR_NOT_ENOUGH_CORRESPONDENCES: return "ICP loop ended early: not enough correspondences";
+    default: return "ICP loop failed";
+  }
+}
+
+// Enqueue getFitnessScore for slot i (result lands in states[i].fitness_*).
+int enqueue_fitness(b2icp_handle* h, int i, double max_range) {
+  ScanSlot& s = slot(h, i);
+  GridSlot& g = gslot(h, s.grid);
+  const size_t n = s.src.n;
+  CK(h->query.ensure(n * sizeof(float4)));
+  CK(h->q_idx.ensure(n * sizeof(int)));
+  CK(h->q_d2.ensure(n * sizeof(float)));
+  CK(h->unres_list.ensure(n * sizeof(int)));
+  zero_counter<<<1, 1, 0, h->stream>>>(h->unres_count.as<unsigned int>());
+  dim3 grid((unsigned)((n + kSweepThreads - 1) / kSweepThreads), 1, 1);
+  fitness_kernel<<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>() + i, kUnboundedRings,
+                                                        h->unres_list.as<int>(), h->unres_count.as<unsigned int>(),
+                                                        h->query.as<float4>(), h->q_idx.as<int>(), h->q_d2.as<float>());
+  nn_brute_fallback<<<148 * 2, 256, 0, h->stream>>>(g.view, h->query.as<float4>(), h->unres_list.as<int>(),
+                                                    h->unres_count.as<unsigned int>(), h->q_idx.as<int>(),
+                                                    h->q_d2.as<float>());
+  fitness_reduce<<<1, 1024, 0, h->stream>>>(h->q_idx.as<int>(), h->q_d2.as<float>(), (int)n, max_range,
+                                            h->states.as<IcpState>() + i);
+  h->launches += 4;
+  return B2ICP_OK;
+}
+
+double fitness_value(const IcpState& s) {
+  return s.fitness_cnt > 0 ? s.fitness_sum / (double)s.fitness_cnt : DBL_MAX;
+}
+
 int nn_search_impl(b2icp_handle* h, const float4* d_q, size_t n, int* d_idx, float* d_d2) {
+  GridSlot& g = gslot(h, 0);
   CK(h->unres_list.ensure(n * sizeof(int)));
   zero_counter<<<1, 1, 0, h->stream>>>(h->unres_count.as<unsigned int>());
   nn_search_kernel<<<(unsigned)((n + kSweepThreads - 1) / kSweepThreads), kSweepThreads, 0, h->stream>>>(
-      h->grid.view, d_q, (int)n, INFINITY, kUnboundedRings, d_idx, d_d2, h->unres_list.as<int>(),
+      g.view, d_q, (int)n, INFINITY, kUnboundedRings, d_idx, d_d2, h->unres_list.as<int>(),
       h->unres_count.as<unsigned int>());
-  nn_brute_fallback<<<148 * 2, 256, 0, h->stream>>>(h->grid.view, d_q, h->unres_list.as<int>(),
+  nn_brute_fallback<<<148 * 2, 256, 0, h->stream>>>(g.view, d_q, h->unres_list.as<int>(),
                                                     h->unres_count.as<unsigned int>(), d_idx, d_d2);
+  h->launches += 3;
   return B2ICP_OK;
+}
+
+int batch_impl(b2icp_handle* h, const float* const* src, const size_t* n_src, const float* const* tgt,
+               const size_t* n_tgt, size_t batch, int with_fitness, b2icp_result* out, bool from_device) {
+  for (size_t i = 0; i < batch; ++i) identity_result(&out[i]);
+  if (batch == 0) return B2ICP_OK;
+  const bool shared_target = (tgt == nullptr);
+  if (shared_target && !gslot(h, 0).valid) return fail(h, B2ICP_ERR_NO_TARGET, "no target cloud set");
+  if (!shared_target && !tgt[0] && !gslot(h, 0).valid) return fail(h, B2ICP_ERR_NO_TARGET, "pair 0 has no target");
+  int worst = B2ICP_OK;
+  h->aligned = false;
+  // In consecutive-sweep mode pair i (tgt[i] == NULL) registers against src[i-1]; across chunk borders the
+  // predecessor's device copy is handed over to the next chunk's first grid slot.
+  for (size_t base = 0; base < batch; base += kMaxBatch) {
+    const int B = (int)std::min<size_t>(kMaxBatch, batch - base);
+    const bool carry = !shared_target && base > 0 && !tgt[base];
+    if (carry) {
+      GridSlot& g1 = gslot(h, 1);
+      ScanSlot& last = slot(h, kMaxBatch - 1);
+      std::swap(g1.tgt.raw, last.src.raw);
+      g1.tgt.n = last.src.n;
+      g1.tgt.valid = true;
+      last.src.valid = false;
+    }
+    // 1. upload sources
+    for (int i = 0; i < B; ++i) {
+      int rc = upload_cloud(h, slot(h, i).src, src[base + i], n_src[base + i], from_device);
+      if (rc) return rc;
+    }
+    // 2. targets / grids
+    if (shared_target) {
+      for (int i = 0; i < B; ++i) slot(h, i).grid = 0;
+    } else {
+      std::vector<GridSlot*> gl;
+      std::vector<size_t> nl;
+      for (int i = 0; i < B; ++i) {
+        const size_t gi = 1 + (size_t)i;  // grid 0 stays the handle's own target
+        GridSlot& g = gslot(h, gi);
+        const float* tp = tgt[base + i];
+        size_t tn = 0;
+        if (tp) {
+          tn = n_tgt ? n_tgt[base + i] : 0;
+          int rc = upload_cloud(h, g.tgt, tp, tn, from_device);
+          if (rc) return rc;
+          g.pts = g.tgt.raw.as<float4>();
+        } else if (i > 0) {
+          g.pts = slot(h, i - 1).src.raw.as<float4>();
+          tn = slot(h, i - 1).src.n;
+        } else if (carry) {
+          g.pts = g.tgt.raw.as<float4>();
+          tn = g.tgt.n;
+        } else {
+          slot(h, i).grid = 0;  // pair 0 without a target: the handle's current target
+          continue;
+        }
+        slot(h, i).grid = (int)gi;
+        gl.push_back(&g);
+        nl.push_back(tn);
+      }
+      if (!gl.empty()) {
+        int rc = build_grids(h, gl.data(), nl.data(), (int)gl.size());
+        if (rc) return rc;
+      }
+    }
+    // 3. the ICP loops of the whole chunk
+    int rc = run_batch(h, B, nullptr);
+    if (rc) return rc;
+    if (with_fitness)
+      for (int i = 0; i < B; ++i) {
+        rc = enqueue_fitness(h, i, DBL_MAX);
+        if (rc) return rc;
+      }
+    rc = read_states(h, B);
+    if (rc) return rc;
+    for (int i = 0; i < B; ++i) {
+      fill_result(h->h_states[i], &out[base + i]);
+      if (with_fitness && h->h_states[i].status == 0) out[base + i].fitness = fitness_value(h->h_states[i]);
+      if (h->h_states[i].status != 0 && worst == B2ICP_OK) {
+        worst = h->h_states[i].status;
+        h->err = status_message(worst);
+      }
+    }
+  }
+  return worst;
 }
 
 }  // namespace
@@ -435,13 +609,16 @@ int b2icp_create(const b2icp_params* p, b2icp_handle** out) {
   h->device = p->device;
   std::memset(&h->timing, 0, sizeof(h->timing));
   derive_config(h);
+  slot(h, 0);
+  gslot(h, 0);
   bool ok = cudaSetDevice(h->device) == cudaSuccess &&
             cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess &&
-            cudaMallocHost((void**)&h->h_state, sizeof(IcpState)) == cudaSuccess &&
-            cudaMallocHost((void**)&h->h_bbox, sizeof(BBox)) == cudaSuccess &&
-            h->state.ensure(sizeof(IcpState)) == cudaSuccess && h->tasks.ensure(sizeof(ScanTask)) == cudaSuccess &&
-            h->bbox.ensure(sizeof(BBox)) == cudaSuccess && h->unres_count.ensure(sizeof(unsigned int)) == cudaSuccess &&
-            h->mat.ensure(16 * sizeof(double)) == cudaSuccess;
+            cudaMallocHost((void**)&h->h_states, sizeof(IcpState) * kMaxBatch) == cudaSuccess &&
+            cudaMallocHost((void**)&h->h_tasks, sizeof(ScanTask) * kMaxBatch) == cudaSuccess &&
+            cudaMallocHost((void**)&h->h_bbox, sizeof(BBox) * (kMaxBatch + 1)) == cudaSuccess &&
+            h->states.ensure(sizeof(IcpState) * kMaxBatch) == cudaSuccess &&
+            h->tasks.ensure(sizeof(ScanTask) * kMaxBatch) == cudaSuccess &&
+            h->unres_count.ensure(sizeof(unsigned int)) == cudaSuccess && h->mat.ensure(16 * sizeof(double)) == cudaSuccess;
   if (!ok) {
     cudaGetLastError();
     b2icp_destroy(h);
@@ -455,15 +632,28 @@ int b2icp_destroy(b2icp_handle* h) {
   if (!h) return B2ICP_ERR_INVALID_ARG;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  for (DeviceBuf* b : {&h->src.raw, &h->tgt.raw, &h->grid.sorted, &h->grid.cell_start, &h->grid.cell_of, &h->grid.rank,
-                       &h->cur, &h->corr_idx, &h->corr_d2, &h->partials, &h->state, &h->tasks, &h->bbox, &h->tile_sums,
-                       &h->unres_list, &h->unres_count, &h->query, &h->q_idx, &h->q_d2, &h->xf_in, &h->xf_out, &h->mat})
+  for (auto& s : h->slots) s->release();
+  for (auto& g : h->grids) g->release();
+  for (DeviceBuf* b : {&h->states, &h->tasks, &h->unres_list, &h->unres_count, &h->query, &h->q_idx, &h->q_d2, &h->xf_in,
+                       &h->xf_out, &h->mat})
     b->release();
   for (cudaEvent_t e : h->events) cudaEventDestroy(e);
-  if (h->h_state) cudaFreeHost(h->h_state);
+  if (h->h_states) cudaFreeHost(h->h_states);
+  if (h->h_tasks) cudaFreeHost(h->h_tasks);
   if (h->h_bbox) cudaFreeHost(h->h_bbox);
-  if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
+  return B2ICP_OK;
+}
+
+int b2icp_set_stream(b2icp_handle* h, void* cuda_stream) {
+  if (!h) return B2ICP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->stream));
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  h->stream = static_cast<cudaStream_t>(cuda_stream);
+  h->own_stream = false;
   return B2ICP_OK;
 }
 
@@ -480,41 +670,51 @@ int b2icp_set_target(b2icp_handle* h, const float* xyzw, size_t n) {
   if (!h) return B2ICP_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lk(h->mu);
   CK(cudaSetDevice(h->device));
-  return set_target_impl(h, xyzw, n, false);
+  return set_target_impl(h, 0, xyzw, n, false);
 }
 int b2icp_set_target_device(b2icp_handle* h, const float* d_xyzw, size_t n) {
   if (!h) return B2ICP_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lk(h->mu);
   CK(cudaSetDevice(h->device));
-  return set_target_impl(h, d_xyzw, n, true);
+  return set_target_impl(h, 0, d_xyzw, n, true);
 }
 int b2icp_set_source(b2icp_handle* h, const float* xyzw, size_t n) {
   if (!h) return B2ICP_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lk(h->mu);
   CK(cudaSetDevice(h->device));
-  return set_source_impl(h, xyzw, n, false);
+  h->aligned = false;
+  slot(h, 0).src.valid = false;
+  slot(h, 0).grid = 0;
+  return upload_cloud(h, slot(h, 0).src, xyzw, n, false);
 }
 int b2icp_set_source_device(b2icp_handle* h, const float* d_xyzw, size_t n) {
   if (!h) return B2ICP_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lk(h->mu);
   CK(cudaSetDevice(h->device));
-  return set_source_impl(h, d_xyzw, n, true);
+  h->aligned = false;
+  slot(h, 0).src.valid = false;
+  slot(h, 0).grid = 0;
+  return upload_cloud(h, slot(h, 0).src, d_xyzw, n, true);
 }
 
 int b2icp_promote_source_to_target(b2icp_handle* h) {
   if (!h) return B2ICP_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lk(h->mu);
   CK(cudaSetDevice(h->device));
-  if (!h->src.valid) return fail(h, B2ICP_ERR_NO_SOURCE, "no source cloud set");
-  std::swap(h->src.raw, h->tgt.raw);
-  h->tgt.n = h->src.n;
-  h->tgt.valid = true;
-  h->src.valid = false;
-  h->src.n = 0;
+  ScanSlot& s = slot(h, 0);
+  GridSlot& g = gslot(h, 0);
+  if (!s.src.valid) return fail(h, B2ICP_ERR_NO_SOURCE, "no source cloud set");
+  std::swap(s.src.raw, g.tgt.raw);
+  g.tgt.n = s.src.n;
+  g.tgt.valid = true;
+  g.pts = g.tgt.raw.as<float4>();
+  s.src.valid = false;
+  s.src.n = 0;
   h->aligned = false;
-  h->grid.valid = false;
-  int rc = build_grid(h);
-  if (rc) h->tgt.valid = false;
+  GridSlot* gp = &g;
+  size_t n = g.tgt.n;
+  int rc = build_grids(h, &gp, &n, 1);
+  if (rc) g.tgt.valid = false;
   return rc;
 }
 
@@ -522,7 +722,32 @@ int b2icp_align(b2icp_handle* h, const float* guess, b2icp_result* out, float* a
   if (!h) return B2ICP_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lk(h->mu);
   CK(cudaSetDevice(h->device));
-  return align_impl(h, guess, out, aligned_xyzw);
+  if (!out) return fail(h, B2ICP_ERR_INVALID_ARG, "out == NULL");
+  identity_result(out);
+  ScanSlot& s = slot(h, 0);
+  s.grid = 0;
+  if (!s.src.valid) return fail(h, B2ICP_ERR_NO_SOURCE, "no source cloud set");
+  if (!gslot(h, 0).valid) return fail(h, B2ICP_ERR_NO_TARGET, "no target cloud set");
+  h->aligned = false;
+  int rc = run_batch(h, 1, guess);
+  if (rc) return rc;
+  const size_t n = s.src.n;
+  if (aligned_xyzw) {
+    CK(h->xf_out.ensure(n * sizeof(float4)));
+    transform_cloud_f<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(
+        s.src.raw.as<float4>(), (int)n, h->states.as<IcpState>()->final_T, h->xf_out.as<float4>());
+    h->launches += 1;
+    CK(cudaMemcpyAsync(aligned_xyzw, h->xf_out.p, n * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+  }
+  rc = read_states(h, 1);
+  if (rc) return rc;
+  fill_result(h->h_states[0], out);
+  h->aligned = true;
+  if (h->h_states[0].status != 0) {
+    h->err = status_message(h->h_states[0].status);
+    return h->h_states[0].status;
+  }
+  return B2ICP_OK;
 }
 
 int b2icp_fitness(b2icp_handle* h, double max_range, double* out) {
@@ -530,24 +755,12 @@ int b2icp_fitness(b2icp_handle* h, double max_range, double* out) {
   std::lock_guard<std::mutex> lk(h->mu);
   CK(cudaSetDevice(h->device));
   if (!h->aligned) return fail(h, B2ICP_ERR_NOT_ALIGNED, "b2icp_fitness needs a completed b2icp_align");
-  const size_t n = h->src.n;
-  CK(h->query.ensure(n * sizeof(float4)));
-  CK(h->q_idx.ensure(n * sizeof(int)));
-  CK(h->q_d2.ensure(n * sizeof(float)));
-  zero_counter<<<1, 1, 0, h->stream>>>(h->unres_count.as<unsigned int>());
-  dim3 grid((unsigned)((n + kSweepThreads - 1) / kSweepThreads), 1, 1);
-  fitness_kernel<<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>(), kUnboundedRings, max_range,
-                                                        h->unres_list.as<int>(), h->unres_count.as<unsigned int>(),
-                                                        h->query.as<float4>(), h->q_idx.as<int>(), h->q_d2.as<float>());
-  nn_brute_fallback<<<148 * 2, 256, 0, h->stream>>>(h->grid.view, h->query.as<float4>(), h->unres_list.as<int>(),
-                                                    h->unres_count.as<unsigned int>(), h->q_idx.as<int>(),
-                                                    h->q_d2.as<float>());
-  fitness_reduce<<<1, 1024, 0, h->stream>>>(h->q_idx.as<int>(), h->q_d2.as<float>(), (int)n, max_range,
-                                            h->state.as<IcpState>());
-  CK(cudaMemcpyAsync(h->h_state, h->state.p, sizeof(IcpState), cudaMemcpyDeviceToHost, h->stream));
+  int rc = enqueue_fitness(h, 0, max_range);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h->h_states, h->states.p, sizeof(IcpState), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
-  *out = h->h_state->fitness_cnt > 0 ? h->h_state->fitness_sum / (double)h->h_state->fitness_cnt : DBL_MAX;
+  *out = fitness_value(h->h_states[0]);
   return B2ICP_OK;
 }
 
@@ -556,9 +769,10 @@ int b2icp_get_correspondences(b2icp_handle* h, int32_t* tgt_idx, float* sqdist) 
   std::lock_guard<std::mutex> lk(h->mu);
   CK(cudaSetDevice(h->device));
   if (!h->aligned) return fail(h, B2ICP_ERR_NOT_ALIGNED, "no completed b2icp_align");
-  const size_t n = h->src.n;
-  if (tgt_idx) CK(cudaMemcpyAsync(tgt_idx, h->corr_idx.p, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-  if (sqdist) CK(cudaMemcpyAsync(sqdist, h->corr_d2.p, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  ScanSlot& s = slot(h, 0);
+  const size_t n = s.src.n;
+  if (tgt_idx) CK(cudaMemcpyAsync(tgt_idx, s.corr_idx.p, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (sqdist) CK(cudaMemcpyAsync(sqdist, s.corr_d2.p, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return B2ICP_OK;
 }
@@ -567,7 +781,7 @@ int b2icp_nn_search(b2icp_handle* h, const float* q_xyzw, size_t n, int32_t* idx
   if (!h || !idx) return B2ICP_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lk(h->mu);
   CK(cudaSetDevice(h->device));
-  if (!h->tgt.valid || !h->grid.valid) return fail(h, B2ICP_ERR_NO_TARGET, "no target cloud set");
+  if (!gslot(h, 0).valid) return fail(h, B2ICP_ERR_NO_TARGET, "no target cloud set");
   if (n == 0) return B2ICP_OK;
   if (!q_xyzw) return fail(h, B2ICP_ERR_INVALID_ARG, "q_xyzw == NULL");
   CK(h->query.ensure(n * sizeof(float4)));
@@ -587,7 +801,7 @@ int b2icp_nn_search_device(b2icp_handle* h, const float* d_q_xyzw, size_t n, int
   if (!h || !d_idx || !d_sqdist) return B2ICP_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lk(h->mu);
   CK(cudaSetDevice(h->device));
-  if (!h->tgt.valid || !h->grid.valid) return fail(h, B2ICP_ERR_NO_TARGET, "no target cloud set");
+  if (!gslot(h, 0).valid) return fail(h, B2ICP_ERR_NO_TARGET, "no target cloud set");
   if (n == 0) return B2ICP_OK;
   if (!d_q_xyzw) return fail(h, B2ICP_ERR_INVALID_ARG, "d_q_xyzw == NULL");
   const bool prof = h->params.profile != 0;
@@ -612,6 +826,7 @@ int b2icp_nn_search_device(b2icp_handle* h, const float* d_q_xyzw, size_t n, int
     h->timing.nn_sweep_ms = ms;
     h->timing.total_ms = ms;
   }
+  h->timing.kernel_launches = h->launches;
   return B2ICP_OK;
 }
 
@@ -627,6 +842,7 @@ static int transform_impl(b2icp_handle* h, const float* in, size_t n, const void
     transform_cloud_d<<<blocks, 256, 0, h->stream>>>(h->xf_in.as<float4>(), (int)n, h->mat.as<double>(), h->xf_out.as<float4>());
   else
     transform_cloud_f<<<blocks, 256, 0, h->stream>>>(h->xf_in.as<float4>(), (int)n, h->mat.as<float>(), h->xf_out.as<float4>());
+  h->launches += 1;
   CK(cudaMemcpyAsync(out, h->xf_out.p, n * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   CK(cudaGetLastError());
@@ -651,54 +867,22 @@ int b2icp_align_batch(b2icp_handle* h, const float* const* src, const size_t* n_
   if (!h || !src || !n_src || !out) return B2ICP_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lk(h->mu);
   CK(cudaSetDevice(h->device));
-  int worst = B2ICP_OK;
-  for (size_t i = 0; i < batch; ++i) {
-    identity_result(&out[i]);
-    int rc = B2ICP_OK;
-    if (tgt && tgt[i]) {
-      rc = set_target_impl(h, tgt[i], n_tgt ? n_tgt[i] : 0, false);
-    } else if (i > 0 && h->src.valid) {
-      // consecutive-sweep odometry: the previous source becomes the target (icp_odometer.cpp:209)
-      std::swap(h->src.raw, h->tgt.raw);
-      h->tgt.n = h->src.n;
-      h->tgt.valid = true;
-      h->src.valid = false;
-      h->grid.valid = false;
-      rc = build_grid(h);
-    } else if (!h->tgt.valid) {
-      rc = fail(h, B2ICP_ERR_NO_TARGET, "pair 0 has no target");
-    }
-    if (!rc) rc = set_source_impl(h, src[i], n_src[i], false);
-    if (!rc) rc = align_impl(h, nullptr, &out[i], nullptr);
-    if (!rc && with_fitness) {
-      // inline fitness (same sequence as b2icp_fitness)
-      const size_t n = h->src.n;
-      CK(h->query.ensure(n * sizeof(float4)));
-      CK(h->q_idx.ensure(n * sizeof(int)));
-      CK(h->q_d2.ensure(n * sizeof(float)));
-      zero_counter<<<1, 1, 0, h->stream>>>(h->unres_count.as<unsigned int>());
-      dim3 grid((unsigned)((n + kSweepThreads - 1) / kSweepThreads), 1, 1);
-      fitness_kernel<<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>(), kUnboundedRings, DBL_MAX,
-                                                            h->unres_list.as<int>(), h->unres_count.as<unsigned int>(),
-                                                            h->query.as<float4>(), h->q_idx.as<int>(), h->q_d2.as<float>());
-      nn_brute_fallback<<<148 * 2, 256, 0, h->stream>>>(h->grid.view, h->query.as<float4>(), h->unres_list.as<int>(),
-                                                        h->unres_count.as<unsigned int>(), h->q_idx.as<int>(),
-                                                        h->q_d2.as<float>());
-      fitness_reduce<<<1, 1024, 0, h->stream>>>(h->q_idx.as<int>(), h->q_d2.as<float>(), (int)n, DBL_MAX,
-                                                h->state.as<IcpState>());
-      CK(cudaMemcpyAsync(h->h_state, h->state.p, sizeof(IcpState), cudaMemcpyDeviceToHost, h->stream));
-      CK(cudaStreamSynchronize(h->stream));
-      out[i].fitness = h->h_state->fitness_cnt > 0 ? h->h_state->fitness_sum / (double)h->h_state->fitness_cnt : DBL_MAX;
-    }
-    if (rc && !worst) worst = rc;
-    out[i].status_detail = rc;
-  }
-  return worst;
+  return batch_impl(h, src, n_src, tgt, n_tgt, batch, with_fitness, out, false);
+}
+
+int b2icp_align_batch_device(b2icp_handle* h, const float* const* d_src, const size_t* n_src,
+                             const float* const* d_tgt, const size_t* n_tgt, size_t batch, int with_fitness,
+                             b2icp_result* out) {
+  if (!h || !d_src || !n_src || !out) return B2ICP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CK(cudaSetDevice(h->device));
+  return batch_impl(h, d_src, n_src, d_tgt, n_tgt, batch, with_fitness, out, true);
 }
 
 int b2icp_get_timing(b2icp_handle* h, b2icp_timing* out) {
   if (!h || !out) return B2ICP_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lk(h->mu);
+  h->timing.kernel_launches = h->launches;
   *out = h->timing;
   return B2ICP_OK;
 }
@@ -706,14 +890,15 @@ int b2icp_get_timing(b2icp_handle* h, b2icp_timing* out) {
 int b2icp_get_grid_info(b2icp_handle* h, float* cell, int32_t* dims3, double* occupancy) {
   if (!h) return B2ICP_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lk(h->mu);
-  if (!h->grid.valid) return fail(h, B2ICP_ERR_NO_TARGET, "no target cloud set");
-  if (cell) *cell = h->grid.view.cell;
+  GridSlot& g = gslot(h, 0);
+  if (!g.valid) return fail(h, B2ICP_ERR_NO_TARGET, "no target cloud set");
+  if (cell) *cell = g.view.cell;
   if (dims3) {
-    dims3[0] = h->grid.view.nx;
-    dims3[1] = h->grid.view.ny;
-    dims3[2] = h->grid.view.nz;
+    dims3[0] = g.view.nx;
+    dims3[1] = g.view.ny;
+    dims3[2] = g.view.nz;
   }
-  if (occupancy) *occupancy = h->grid.occupancy;
+  if (occupancy) *occupancy = g.occupancy;
   return B2ICP_OK;
 }
 

@@ -63,6 +63,7 @@ struct ScanTask {
   float4* cur;         // input_transformed: rewritten in place by every sweep
   int* corr_idx;       // [n] target index of the last sweep, -1 = gated out
   float* corr_d2;      // [n] float d2 of the last sweep
+  int* corr_pos;       // [n] sorted-array position of the last match (seed of the next search), -1 = none
   double* partials;    // [gridDim.x][kNumSums] per-CTA sums
   IcpState* state;
   int n;

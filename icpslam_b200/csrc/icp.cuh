@@ -93,13 +93,14 @@ __global__ void __launch_bounds__(kSweepThreads) icp_sweep_p2p(const ScanTask* _
     r.key = kInfKey;
     r.pos = -1;
     if (isfinite(q.x) && isfinite(q.y) && isfinite(q.z))
-      r = grid_nn(t.grid, q.x, q.y, q.z, cfg.bound2, cfg.max_rings);
+      r = grid_nn(t.grid, q.x, q.y, q.z, cfg.bound2, cfg.max_rings, first ? -1 : t.corr_pos[i]);
     else
       atomicOr(&st->pad, 1);  // non-finite source point or transform: reported by the last CTA
     const float d2 = key_d2(r.key);
     const bool keep = (r.key != kInfKey) && !((double)d2 > cfg.max2);
     t.corr_idx[i] = keep ? key_idx(r.key) : -1;
     t.corr_d2[i] = d2;
+    t.corr_pos[i] = r.pos;
     if (keep) {
       const float4 m = __ldg(t.grid.pts + r.pos);
       const double sx = q.x, sy = q.y, sz = q.z, dx = m.x, dy = m.y, dz = m.z;
@@ -121,13 +122,13 @@ __global__ void __launch_bounds__(kSweepThreads) icp_sweep_p2p(const ScanTask* _
 }
 
 // ---- getFitnessScore(max_range): transform by final_T, exact unbounded 1-NN, mean of d2 <= range
-__global__ void __launch_bounds__(kSweepThreads) fitness_kernel(const ScanTask* __restrict__ tasks, int max_rings,
-                                                                double max_range, int* __restrict__ unresolved_list,
+__global__ void __launch_bounds__(kSweepThreads) fitness_kernel(const ScanTask* __restrict__ task, int max_rings,
+                                                                int* __restrict__ unresolved_list,
                                                                 unsigned int* __restrict__ unresolved_count,
                                                                 float4* __restrict__ q_out, int* __restrict__ idx_out,
                                                                 float* __restrict__ d2_out) {
   __shared__ float sT[16];
-  const ScanTask& t = tasks[blockIdx.y];
+  const ScanTask& t = *task;
   if (threadIdx.x < 16) sT[threadIdx.x] = t.state->final_T[threadIdx.x];
   __syncthreads();
   const int i = blockIdx.x * kSweepThreads + threadIdx.x;

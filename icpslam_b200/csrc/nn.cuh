@@ -47,8 +47,10 @@ __device__ __forceinline__ void scan_range(const float4* __restrict__ pts, int s
   }
 }
 
+// `seed_pos` >= 0: sorted position of a target point already known to be close (the previous
+// iteration's match).  It only tightens the pruning threshold; the result is still the exact NN.
 __device__ __forceinline__ NNResult grid_nn(const GridView& g, float qx, float qy, float qz, float bound2,
-                                            int max_rings) {
+                                            int max_rings, int seed_pos = -1) {
   NNResult r;
   r.key = kInfKey;
   r.pos = -1;
@@ -57,24 +59,44 @@ __device__ __forceinline__ NNResult grid_nn(const GridView& g, float qx, float q
   const int cy = cell_coord(qy, g.oy, g.inv_cell, g.ny);
   const int cz = cell_coord(qz, g.oz, g.inv_cell, g.nz);
   float thr = bound2;
+  if (seed_pos >= 0) {
+    const float4 p = __ldg(g.pts + seed_pos);
+    r.key = pack_key(sqdist3(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w));
+    r.pos = seed_pos;
+    thr = fminf(bound2, key_d2(r.key));
+  }
 
-  // ---- 3x3x3 block: centre row, then the 4 edge-adjacent rows, then the 4 corner rows
+  // ---- 3x3x3 block: centre row, then the 4 edge-adjacent rows, then the 4 corner rows; inside a
+  // row the three cells are pruned one by one against thr
   {
-    const int xa = max(cx - 1, 0), xb = min(cx + 1, g.nx - 1);
+    // conservative x-gaps to the left / right neighbour cells (0 for the own cell)
+    const float gxl = fmaxf(qx - (g.ox + (float)cx * g.cell) - g.slack, 0.0f);
+    const float gxr = fmaxf((g.ox + (float)(cx + 1) * g.cell) - qx - g.slack, 0.0f);
+    const float gxl2 = fmul(gxl, gxl), gxr2 = fmul(gxr, gxr);
+    const bool has_l = cx > 0, has_r = cx < g.nx - 1;
 #pragma unroll
     for (int t = 0; t < 9; ++t) {
       const int dy = (t == 1 || t == 5 || t == 7) ? -1 : ((t == 2 || t == 6 || t == 8) ? 1 : 0);
       const int dz = (t == 3 || t == 5 || t == 6) ? -1 : ((t == 4 || t == 7 || t == 8) ? 1 : 0);
       const int y = cy + dy, z = cz + dz;
       if (y < 0 || y >= g.ny || z < 0 || z >= g.nz) continue;
-      float ly = slab_gap(qy, g.oy, g.cell, y, y, g.slack);
-      float lz = slab_gap(qz, g.oz, g.cell, z, z, g.slack);
-      float lb = fadd(fmul(ly, ly), fmul(lz, lz));
+      const float ly = slab_gap(qy, g.oy, g.cell, y, y, g.slack);
+      const float lz = slab_gap(qz, g.oz, g.cell, z, z, g.slack);
+      const float ly2 = fmul(ly, ly), lz2 = fmul(lz, lz);
+      const float lb = fadd(ly2, lz2);
       if (lb > thr) continue;
-      const int row = (z * g.ny + y) * g.nx;
-      const int s = __ldg(g.cell_start + row + xa), e = __ldg(g.cell_start + row + xb + 1);
-      scan_range(g.pts, s, e, qx, qy, qz, r.key, r.pos);
+      const int* cs = g.cell_start + (z * g.ny + y) * g.nx + cx;
+      const int s0 = __ldg(cs), s1 = __ldg(cs + 1);
+      scan_range(g.pts, s0, s1, qx, qy, qz, r.key, r.pos);
       thr = fminf(bound2, key_d2(r.key));
+      if (has_l && !(fadd(fadd(gxl2, ly2), lz2) > thr)) {
+        scan_range(g.pts, __ldg(cs - 1), s0, qx, qy, qz, r.key, r.pos);
+        thr = fminf(bound2, key_d2(r.key));
+      }
+      if (has_r && !(fadd(fadd(gxr2, ly2), lz2) > thr)) {
+        scan_range(g.pts, s1, __ldg(cs + 2), qx, qy, qz, r.key, r.pos);
+        thr = fminf(bound2, key_d2(r.key));
+      }
     }
   }
 

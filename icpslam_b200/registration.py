@@ -81,8 +81,8 @@ class Timing(C.Structure):
         ("nn_sweep_ms", C.c_double),
         ("build_ms", C.c_double),
         ("total_ms", C.c_double),
-        ("nn_candidates", C.c_uint64),
-        ("nt_touched", C.c_uint64),
+        ("kernel_launches", C.c_int64),
+        ("reserved2", C.c_uint64),
     ]
 
 
@@ -90,7 +90,8 @@ EXPORTS = [
     "b2icp_default_params", "b2icp_create", "b2icp_destroy", "b2icp_set_params", "b2icp_set_target",
     "b2icp_set_source", "b2icp_set_target_device", "b2icp_set_source_device", "b2icp_promote_source_to_target",
     "b2icp_align", "b2icp_fitness", "b2icp_get_correspondences", "b2icp_nn_search", "b2icp_nn_search_device",
-    "b2icp_transform_cloud", "b2icp_transform_cloud_f", "b2icp_align_batch", "b2icp_get_timing",
+    "b2icp_transform_cloud", "b2icp_transform_cloud_f", "b2icp_align_batch", "b2icp_align_batch_device",
+    "b2icp_set_stream", "b2icp_get_timing",
     "b2icp_get_grid_info", "b2icp_host_alloc", "b2icp_host_free", "b2icp_last_error", "b2icp_status_string",
     "b2icp_version",
 ]
@@ -127,6 +128,8 @@ def load_library() -> C.CDLL:
     L.b2icp_transform_cloud_f.argtypes = [vp, vp, C.c_size_t, fp, vp]
     L.b2icp_align_batch.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(vp), C.POINTER(C.c_size_t),
                                     C.c_size_t, C.c_int, C.POINTER(Result)]
+    L.b2icp_align_batch_device.argtypes = L.b2icp_align_batch.argtypes
+    L.b2icp_set_stream.argtypes = [vp, vp]
     L.b2icp_get_timing.argtypes = [vp, C.POINTER(Timing)]
     L.b2icp_get_grid_info.argtypes = [vp, fp, ip, dp]
     L.b2icp_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
@@ -322,17 +325,34 @@ class Registration:
         return out
 
     def alignBatch(self, sources, targets=None, with_fitness: bool = False):
-        """b2icp_align_batch: targets[i] None => sources[i-1] is the target (consecutive sweeps)."""
+        """b2icp_align_batch.  targets=None: every source against the current target (resident map);
+        targets[i] None (i > 0): sources[i-1] is the target of pair i (consecutive sweeps)."""
         n = len(sources)
         srcs = [_cloud(s) for s in sources]
-        tgts = [None if (targets is None or targets[i] is None) else _cloud(targets[i]) for i in range(n)]
         sp = (C.c_void_p * n)(*[s.ctypes.data for s in srcs])
         sn = (C.c_size_t * n)(*[len(s) for s in srcs])
-        tp = (C.c_void_p * n)(*[(t.ctypes.data if t is not None else None) for t in tgts])
-        tn = (C.c_size_t * n)(*[(len(t) if t is not None else 0) for t in tgts])
         res = (Result * n)()
+        if targets is None:
+            tp = tn = None
+        else:
+            tgts = [None if targets[i] is None else _cloud(targets[i]) for i in range(n)]
+            tp = (C.c_void_p * n)(*[(t.ctypes.data if t is not None else None) for t in tgts])
+            tn = (C.c_size_t * n)(*[(len(t) if t is not None else 0) for t in tgts])
         rc = self._L.b2icp_align_batch(self._h, sp, sn, tp, tn, n, 1 if with_fitness else 0, res)
+        self._n_source = len(srcs[0]) if srcs else 0
         return rc, list(res)
+
+    def alignBatchDevice(self, src_ptrs, n_src, with_fitness: bool = False):
+        """b2icp_align_batch_device against the current target; src_ptrs are device addresses."""
+        n = len(src_ptrs)
+        sp = (C.c_void_p * n)(*src_ptrs)
+        sn = (C.c_size_t * n)(*n_src)
+        res = (Result * n)()
+        rc = self._L.b2icp_align_batch_device(self._h, sp, sn, None, None, n, 1 if with_fitness else 0, res)
+        return rc, list(res)
+
+    def setStream(self, cuda_stream: int):
+        self._check(self._L.b2icp_set_stream(self._h, C.c_void_p(cuda_stream)), "set_stream")
 
     def timing(self) -> Timing:
         t = Timing()

@@ -208,36 +208,126 @@ def local_map(config: int, n_points: int = 500_000, voxel: float = 0.2, n_sweeps
     frame, T_true 4x4 mapping query-frame points into the map frame).  The map is the union of
     sweeps along the trajectory, one point per ``voxel`` cube (first-come), truncated to exactly
     n_points; more sweeps (denser elevation pattern) are added until that many voxels are occupied."""
+    m = build_local_map(config, n_points, voxel, n_sweeps, world_scale)
+    q_pose = m["poses"][m["k"]]
+    query = hdl64_sweep(m["world"], q_pose, np.random.default_rng(1000 * config + 500 + m["k"]))
+    return m["map"], query, m["ref_inv"] @ q_pose
+
+
+def build_local_map(config: int, n_points: int = 500_000, voxel: float = 0.2, n_sweeps: int = 25,
+                    world_scale: float = 1.0, max_batches: int = 200) -> dict:
+    """The map half of ``local_map`` plus what is needed to cast further sweeps against it:
+    dict(map, world, poses, k = index of the first pose after the map, ref_inv = map <- world).
+
+    Union of ``n_sweeps`` HDL-64 sweeps along the trajectory, one point per ``voxel`` cube
+    (first-come wins, insertion order kept — OctreeMapper::addPointsToMap's net effect), then PADDED to
+    exactly ``n_points`` with returns of extra rays cast in random directions from the same poses
+    (the accumulated map of a longer drive), deduplicated the same way, and truncated."""
     world = make_world(1000 * config, world_scale)
-    poses = trajectory(1000 * config + 999, max_sweeps + 1)
-    pts = []
-    total = None
-    k = 0
-    while True:
-        rng = np.random.default_rng(1000 * config + k)
-        if k < n_sweeps:
-            pose_k, beams = poses[k], 64
-        else:  # extra sweeps: denser, pitched elevation pattern so new voxels keep appearing
-            pose_k, beams = poses[k] @ _pitch(rng.normal(0, math.radians(3.0))), 128
-        s = hdl64_sweep(world, pose_k, rng, n_beams=beams)
-        w = s[:, :3].astype(np.float64) @ pose_k[:3, :3].T + pose_k[:3, 3]
-        pts.append(w)
-        k += 1
-        if k >= n_sweeps:
-            total = voxel_dedup_first(np.concatenate(pts), voxel)
-            pts = [total]
-            if len(total) >= n_points or k >= max_sweeps:
-                break
-    total = total[:n_points]
-    if len(total) < n_points:
-        raise RuntimeError(f"local_map: only {len(total)} occupied voxels after {k} sweeps")
+    poses = trajectory(1000 * config + 999, n_sweeps + 1200)
+    lo = np.array([-world.half_x - 1.0, -world.half_y - 1.0, -1.0])
+    dims = np.ceil((np.array([world.half_x, world.half_y, world.height]) + 1.0 - lo) / voxel).astype(np.int64) + 1
+    seen = np.empty(0, dtype=np.int64)  # sorted voxel keys already in the map
+    chunks = []
+    count = 0
+
+    def insert(pw):
+        nonlocal seen, count
+        key3 = np.floor((pw - lo) / voxel).astype(np.int64)
+        key = (key3[:, 2] * dims[1] + key3[:, 1]) * dims[0] + key3[:, 0]
+        _, first = np.unique(key, return_index=True)
+        first.sort()
+        fresh = first[~np.isin(key[first], seen, assume_unique=True)]
+        chunks.append(pw[fresh])
+        seen = np.union1d(seen, key[fresh])
+        count += len(fresh)
+
+    for k in range(n_sweeps):
+        s = hdl64_sweep(world, poses[k], np.random.default_rng(1000 * config + k))
+        insert(s[:, :3].astype(np.float64) @ poses[k][:3, :3].T + poses[k][:3, 3])
+    rng = np.random.default_rng(1000 * config + 777)
+    batches = 0
+    while count < n_points:
+        if batches >= max_batches:
+            raise RuntimeError(f"build_local_map: only {count} occupied voxels after {batches} padding batches")
+        insert(_sample_surfaces(world, rng, 400_000))
+        batches += 1
+    total = np.concatenate(chunks)[:n_points]
+    k = n_sweeps
     ref = poses[k - 1]  # map frame = frame of the last pose that contributed
     ref_inv = np.linalg.inv(ref)
     map_local = total @ ref_inv[:3, :3].T + ref_inv[:3, 3]
-    q_pose = poses[k]
-    query = hdl64_sweep(world, q_pose, np.random.default_rng(1000 * config + 500 + k))
-    T_true = ref_inv @ q_pose
-    return as_xyzw(map_local), query, T_true
+    return dict(map=as_xyzw(map_local), world=world, poses=poses, k=k, ref_inv=ref_inv)
+
+
+def _sample_surfaces(world: World, rng: np.random.Generator, n: int, noise: float = 0.01) -> np.ndarray:
+    """n points drawn area-uniformly from the scene's surfaces (ground, ceiling, walls, box tops and
+    sides, cylinder sides) with isotropic noise: what a long drive would have accumulated."""
+    hx, hy, hz = world.half_x, world.half_y, world.height
+    bs = world.boxes_max - world.boxes_min  # [B,3]
+    areas = [4 * hx * hy, 4 * hx * hy, 4 * hy * hz, 4 * hx * hz]
+    box_top = bs[:, 0] * bs[:, 1]
+    box_sx = 2 * bs[:, 1] * bs[:, 2]  # the two faces normal to x
+    box_sy = 2 * bs[:, 0] * bs[:, 2]
+    cyl = 2 * np.pi * world.cyl_r * world.cyl_h
+    w = np.concatenate([areas, box_top, box_sx, box_sy, cyl])
+    kind = rng.choice(len(w), size=n, p=w / w.sum())
+    u, v, side = rng.uniform(size=n), rng.uniform(size=n), rng.integers(0, 2, n)
+    p = np.zeros((n, 3))
+    nb, nc = len(bs), len(cyl)
+    m = kind == 0  # ground
+    p[m] = np.stack([(2 * u[m] - 1) * hx, (2 * v[m] - 1) * hy, np.zeros(m.sum())], 1)
+    m = kind == 1  # ceiling
+    p[m] = np.stack([(2 * u[m] - 1) * hx, (2 * v[m] - 1) * hy, np.full(m.sum(), hz)], 1)
+    m = kind == 2  # walls x = +-hx
+    p[m] = np.stack([(2 * side[m] - 1) * hx, (2 * u[m] - 1) * hy, v[m] * hz], 1)
+    m = kind == 3  # walls y = +-hy
+    p[m] = np.stack([(2 * u[m] - 1) * hx, (2 * side[m] - 1) * hy, v[m] * hz], 1)
+    k0 = 4
+    m = (kind >= k0) & (kind < k0 + nb)
+    b = kind[m] - k0
+    p[m] = np.stack([world.boxes_min[b, 0] + u[m] * bs[b, 0], world.boxes_min[b, 1] + v[m] * bs[b, 1],
+                     world.boxes_max[b, 2]], 1)
+    k0 += nb
+    m = (kind >= k0) & (kind < k0 + nb)
+    b = kind[m] - k0
+    p[m] = np.stack([np.where(side[m] == 0, world.boxes_min[b, 0], world.boxes_max[b, 0]),
+                     world.boxes_min[b, 1] + u[m] * bs[b, 1], v[m] * bs[b, 2]], 1)
+    k0 += nb
+    m = (kind >= k0) & (kind < k0 + nb)
+    b = kind[m] - k0
+    p[m] = np.stack([world.boxes_min[b, 0] + u[m] * bs[b, 0],
+                     np.where(side[m] == 0, world.boxes_min[b, 1], world.boxes_max[b, 1]), v[m] * bs[b, 2]], 1)
+    k0 += nb
+    m = (kind >= k0) & (kind < k0 + nc)
+    c = kind[m] - k0
+    ang = 2 * np.pi * u[m]
+    p[m] = np.stack([world.cyl_xy[c, 0] + world.cyl_r[c] * np.cos(ang), world.cyl_xy[c, 1] + world.cyl_r[c] * np.sin(ang),
+                     v[m] * world.cyl_h[c]], 1)
+    return p + rng.normal(0.0, noise, p.shape)
+
+
+def map_queries(m: dict, config: int, first: int, count: int, trans_sigma: float = 0.08,
+                rot_sigma_deg: float = 0.4):
+    """``count`` sweeps taken after the map of ``build_local_map``, each already moved into the map
+    frame by its true pose composed with a small odometry error — what
+    OctreeMapper::refineTransformAndGrowMap hands to ICP after `cloud_in_map = raw_pose (x) cloud`
+    (reference src/icpslam/octree_mapper.cpp:136).  Returns (list of float32[N,4], list of the 4x4
+    corrections T_fix with  T_fix * query ~ map)."""
+    out, fixes = [], []
+    for j in range(first, first + count):
+        idx = m["k"] + j
+        pose = m["poses"][idx]
+        rng = np.random.default_rng(1000 * config + 500 + idx)
+        sweep = hdl64_sweep(m["world"], pose, rng)
+        err = np.eye(4)
+        err[:3, :3] = rot_xyz(*np.radians(rng.normal(0, rot_sigma_deg, 3)))
+        err[:3, 3] = np.clip(rng.normal(0, trans_sigma, 3), -0.25, 0.25)
+        T = err @ (m["ref_inv"] @ pose)
+        q = sweep[:, :3].astype(np.float64) @ T[:3, :3].T + T[:3, 3]
+        out.append(as_xyzw(q))
+        fixes.append(np.linalg.inv(err))
+    return out, fixes
 
 
 def _pitch(a: float) -> np.ndarray:

@@ -93,15 +93,16 @@ typedef struct b2icp_result {
   double fitness;        /* NaN unless filled by b2icp_align_fitness / b2icp_fitness */
 } b2icp_result;
 
-/* Accumulated device timings of the last b2icp_align on this handle (profile != 0). */
+/* Device timings of the last b2icp_align / b2icp_align_batch chunk / b2icp_nn_search_device on this
+ * handle (CUDA events on the handle's stream, recorded only when params.profile != 0). */
 typedef struct b2icp_timing {
-  int32_t nn_sweep_launches; /* launches of the fused nn_sweep kernel */
+  int32_t nn_sweep_launches; /* launches of the fused sweep kernel that did work */
   int32_t reserved;
   double nn_sweep_ms;        /* sum of their CUDA-event durations */
-  double build_ms;           /* grid build of source/target done inside align (0 if cached) */
-  double total_ms;           /* first launch -> last launch of align, CUDA events */
-  uint64_t nn_candidates;    /* candidate points examined by the last profiled sweep set */
-  uint64_t nt_touched;       /* N_t' : target points inside cells touched by the last sweep */
+  double build_ms;           /* reserved */
+  double total_ms;           /* first launch -> last launch, CUDA events */
+  int64_t kernel_launches;   /* every kernel this handle has launched since b2icp_create (always filled) */
+  uint64_t reserved2;
 } b2icp_timing;
 
 /* Fill `p` with the reference's constants for one of its two call sites. */
@@ -157,12 +158,28 @@ int b2icp_transform_cloud(b2icp_handle* h, const float* in_xyzw, size_t n, const
 int b2icp_transform_cloud_f(b2icp_handle* h, const float* in_xyzw, size_t n, const float* T,
                             float* out_xyzw);
 
-/* Offline replay: `batch` independent (source, target) pairs, each what one laserCloudCallback
- * does at icp_odometer.cpp:188-201.  If tgt[i] == NULL, pair i uses src[i-1] as its target
- * (consecutive-sweep odometry; the uploaded cloud and its grid are reused on device). */
+/* Offline replay: `batch` independent registrations, each what one laserCloudCallback does at
+ * icp_odometer.cpp:188-201 (or one estimateTransformICP at octree_mapper.cpp:104-117).  Up to 64 scans
+ * advance together: one launch of the fused sweep kernel per ICP iteration serves all of them.
+ *   tgt == NULL          every source registers against the handle's current target (b2icp_set_target):
+ *                        scan-to-map localisation against a resident map;
+ *   tgt[i] != NULL       pair i has its own target cloud of n_tgt[i] points;
+ *   tgt[i] == NULL, i>0  pair i registers against src[i-1] (consecutive-sweep odometry: the uploaded
+ *                        cloud is indexed in place, `*prev_cloud_ = *curr_cloud_` costs nothing);
+ *   tgt[0] == NULL       pair 0 registers against the handle's current target.
+ * with_fitness != 0 also fills out[i].fitness (getFitnessScore()).  Returns the first non-zero
+ * per-scan status (each out[i].status_detail holds its own). */
 int b2icp_align_batch(b2icp_handle* h, const float* const* src, const size_t* n_src,
                       const float* const* tgt, const size_t* n_tgt, size_t batch,
                       int with_fitness, b2icp_result* out);
+/* Same with every cloud pointer in device memory of the handle's device. */
+int b2icp_align_batch_device(b2icp_handle* h, const float* const* d_src, const size_t* n_src,
+                             const float* const* d_tgt, const size_t* n_tgt, size_t batch,
+                             int with_fitness, b2icp_result* out);
+
+/* Run all work of this handle on the caller's CUDA stream (a cudaStream_t) instead of the private one,
+ * so that device-resident pipelines can order their own kernels and events around the ABI calls. */
+int b2icp_set_stream(b2icp_handle* h, void* cuda_stream);
 
 int b2icp_get_timing(b2icp_handle* h, b2icp_timing* out);
 /* Neighbour grid of the current target (the structure that replaces the FLANN k-d tree): cell edge,

@@ -260,3 +260,40 @@ def test_error_codes(R):
     with pytest.raises(R.B2icpError) as e:
         R.Registration().getFitnessScore()
     assert e.value.code == -10
+
+
+# ------------------------------------------------------------------------------------------------
+# batched execution (one sweep launch per iteration for many scans)
+# ------------------------------------------------------------------------------------------------
+def test_batch_shared_target_equals_single_calls(R, oracle):
+    """tgt == NULL: every source against the resident target; results identical to one-by-one calls."""
+    _, _, sw = synth.sweep_sequence(5, 5, n_beams=64, n_az=256)
+    reg = R.Registration(preset=R.PRESET_MAPPER)
+    reg.setInputTarget(sw[0])
+    singles = []
+    for s in sw[1:]:
+        reg.setInputSource(s)
+        reg.align(raise_on_fail=False)
+        singles.append((reg.getFinalTransformation().copy(), reg.iterations))
+    rc, res = reg.alignBatch(sw[1:], None, with_fitness=True)
+    assert rc == 0
+    for (T, it), r in zip(singles, res):
+        assert r.iterations == it
+        assert np.array_equal(r.matrix(), T)      # same kernels, same order: bit-identical
+        assert r.fitness == r.fitness            # not NaN
+    o = oracle.align(oracle.default_params("mapper"), sw[2], sw[0])
+    assert_transform_close(res[1].matrix(), o["T"])
+
+
+def test_batch_consecutive_pairs_longer_than_one_chunk(R, oracle):
+    """tgt[i] == NULL: pair i registers against src[i-1]; 70 pairs cross the 64-slot chunk border."""
+    _, _, sw = synth.sweep_sequence(6, 6, n_beams=32, n_az=128)
+    seq = [sw[i % 6] for i in range(71)]
+    reg = R.Registration()
+    rc, res = reg.alignBatch(seq[1:], [seq[0]] + [None] * 69)
+    assert rc == 0
+    p = oracle.default_params("odometer")
+    for i in (0, 1, 5, 63, 64, 65, 69):
+        o = oracle.align(p, seq[i + 1], seq[i])
+        assert res[i].iterations == o["iterations"], i
+        assert_transform_close(res[i].matrix(), o["T"])
