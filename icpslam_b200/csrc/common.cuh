@@ -10,7 +10,14 @@
 
 namespace b2 {
 
-constexpr int kSweepThreads = 256;   // CTA size of the fused sweep kernels
+#ifndef B2_SWEEP_THREADS
+#define B2_SWEEP_THREADS 256
+#endif
+#ifndef B2_SWEEP_MIN_CTAS
+#define B2_SWEEP_MIN_CTAS 4
+#endif
+constexpr int kSweepThreads = B2_SWEEP_THREADS;    // CTA size of the fused sweep kernels
+constexpr int kSweepMinCtas = B2_SWEEP_MIN_CTAS;   // resident CTAs per SM the sweep is compiled for
 constexpr int kNumSums = 17;         // n, sum(src)[3], sum(dst)[3], sum(dst*src^T)[9], sum(d2)
 constexpr unsigned long long kInfKey = 0x7F8000007FFFFFFFull;  // d2 = +inf, idx = INT_MAX
 

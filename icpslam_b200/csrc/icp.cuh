@@ -65,8 +65,9 @@ __device__ __forceinline__ bool grid_reduce_last(const ScanTask& t, double (*sme
   return true;
 }
 
-__global__ void __launch_bounds__(kSweepThreads) icp_sweep_p2p(const ScanTask* __restrict__ tasks, IcpConfig cfg) {
+__global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) icp_sweep_p2p(const ScanTask* __restrict__ tasks, IcpConfig cfg) {
   __shared__ double smem[kSweepThreads / 32][kNumSums];
+  __shared__ NNScratch<kSweepThreads> sc;
   __shared__ float sT[16];
   __shared__ int s_flags[2];
   const ScanTask& t = tasks[blockIdx.y];
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(kSweepThreads) icp_sweep_p2p(const ScanTask* _
     r.key = kInfKey;
     r.pos = -1;
     if (isfinite(q.x) && isfinite(q.y) && isfinite(q.z))
-      r = grid_nn(t.grid, q.x, q.y, q.z, cfg.bound2, cfg.max_rings, first ? -1 : t.corr_pos[i]);
+      r = grid_nn<kSweepThreads>(t.grid, q.x, q.y, q.z, cfg.bound2, cfg.max_rings, first ? -1 : t.corr_pos[i], sc);
     else
       atomicOr(&st->pad, 1);  // non-finite source point or transform: reported by the last CTA
     const float d2 = key_d2(r.key);
@@ -128,6 +129,7 @@ __global__ void __launch_bounds__(kSweepThreads) fitness_kernel(const ScanTask* 
                                                                 float4* __restrict__ q_out, int* __restrict__ idx_out,
                                                                 float* __restrict__ d2_out) {
   __shared__ float sT[16];
+  __shared__ NNScratch<kSweepThreads> sc;
   const ScanTask& t = *task;
   if (threadIdx.x < 16) sT[threadIdx.x] = t.state->final_T[threadIdx.x];
   __syncthreads();
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(kSweepThreads) fitness_kernel(const ScanTask* 
   const float4 p = __ldg(t.src + i);
   const float4 q = xform_f(sT, p.x, p.y, p.z);
   q_out[i] = q;
-  NNResult r = grid_nn(t.grid, q.x, q.y, q.z, INFINITY, max_rings);
+  NNResult r = grid_nn<kSweepThreads>(t.grid, q.x, q.y, q.z, INFINITY, max_rings, -1, sc);
   if (!r.resolved) {
     unsigned int slot = atomicAdd(unresolved_count, 1u);
     unresolved_list[slot] = i;

@@ -5,24 +5,39 @@
 // (reference src/icpslam/icp_odometer.cpp:198, src/icpslam/octree_mapper.cpp:114; SURVEY.md
 // App. A.2 step 3, A.3, A.6) and from getFitnessScore() (icp_odometer.cpp:201).
 //
-// Search = ring expansion around the query's cell.  The 3x3x3 block is visited first as nine
-// x-runs of three cells (one contiguous range of the sorted point array each, centre row first);
-// a row is skipped when its conservative lower bound exceeds the running threshold
-// thr = min(best d2, bound2).  Further rings are visited only while the distance from the query to
-// the outside of the block already covered does not exceed thr.  Lower bounds are distances to cell
-// faces minus `slack`, so they can never exceed the float d2 of a point inside the cell: the result
-// is the exact float-arithmetic nearest neighbour with ties on d2 resolved to the smallest original
-// index — bit-identical to the oracle's exhaustive scan.
+// Search order for one query (thr = min(best d2 so far, bound2) is the pruning threshold):
+//   seed      the previous iteration's match, if any: one point load that makes thr tight at once;
+//   phase 0   the query's own cell;
+//   phase 1   the 26 neighbour cells are TESTED (no memory access) against thr with conservative
+//             per-axis face distances; survivors get their [start, end) range loaded and pushed on a
+//             small per-thread list in shared memory — all range loads are independent (MLP);
+//   phase 2   ONE flattened loop pops ranges and scans candidates, so a warp runs for the longest
+//             lane's total work instead of the sum over cells of the per-cell maximum (divergence);
+//   rings     cells at Chebyshev distance >= 2 are visited only while the distance from the query to
+//             the outside of the block already covered does not exceed thr (rare).
+// Lower bounds are distances to cell faces minus `slack`, summed in the association order of the float
+// distance itself, so they can never exceed the float d2 of a point inside the cell: the result is
+// the exact float-arithmetic nearest neighbour, ties on d2 resolved to the smallest original index —
+// bit-identical to the oracle's exhaustive scan.
 #pragma once
 #include "common.cuh"
 #include "grid.cuh"
 
 namespace b2 {
 
+constexpr int kListCap = 12;  // ranges a thread can queue for phase 2; overflow is scanned at once
+
 struct NNResult {
   unsigned long long key;  // pack_key(d2, original target index); kInfKey = nothing found
   int pos;                 // position of that point in the sorted array (GridView::pts)
   bool resolved;           // false: ring budget exhausted before the search could be proven exact
+};
+
+// Per-CTA scratch of the range lists: [kListCap][threads] words, column = thread (conflict-free).
+template <int THREADS>
+struct NNScratch {
+  int start[kListCap][THREADS];
+  unsigned meta[kListCap][THREADS];  // (float bits of lb, truncated) & 0xFFFF0000 | count
 };
 
 // conservative distance from coordinate q to the slab of cells [k_lo, k_hi] on one axis
@@ -35,7 +50,7 @@ __device__ __forceinline__ float slab_gap(float q, float o, float cell, int k_lo
 
 __device__ __forceinline__ void scan_range(const float4* __restrict__ pts, int s, int e, float qx, float qy,
                                            float qz, unsigned long long& best, int& bpos) {
-#pragma unroll 4
+#pragma unroll 2
   for (int j = s; j < e; ++j) {
     float4 p = __ldg(pts + j);
     float d = sqdist3(qx, qy, qz, p.x, p.y, p.z);
@@ -49,8 +64,9 @@ __device__ __forceinline__ void scan_range(const float4* __restrict__ pts, int s
 
 // `seed_pos` >= 0: sorted position of a target point already known to be close (the previous
 // iteration's match).  It only tightens the pruning threshold; the result is still the exact NN.
+template <int THREADS>
 __device__ __forceinline__ NNResult grid_nn(const GridView& g, float qx, float qy, float qz, float bound2,
-                                            int max_rings, int seed_pos = -1) {
+                                            int max_rings, int seed_pos, NNScratch<THREADS>& sc) {
   NNResult r;
   r.key = kInfKey;
   r.pos = -1;
@@ -58,45 +74,95 @@ __device__ __forceinline__ NNResult grid_nn(const GridView& g, float qx, float q
   const int cx = cell_coord(qx, g.ox, g.inv_cell, g.nx);
   const int cy = cell_coord(qy, g.oy, g.inv_cell, g.ny);
   const int cz = cell_coord(qz, g.oz, g.inv_cell, g.nz);
-  float thr = bound2;
+  const int* cs_own = g.cell_start + (cz * g.ny + cy) * g.nx + cx;
+  // issue the own-cell range loads before the seed's dependent point load
+  const int s_own = __ldg(cs_own), e_own = __ldg(cs_own + 1);
   if (seed_pos >= 0) {
     const float4 p = __ldg(g.pts + seed_pos);
     r.key = pack_key(sqdist3(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w));
     r.pos = seed_pos;
-    thr = fminf(bound2, key_d2(r.key));
+  }
+  // ---- phase 0: own cell
+  scan_range(g.pts, s_own, e_own, qx, qy, qz, r.key, r.pos);
+  float thr = fminf(bound2, key_d2(r.key));
+
+  // ---- phase 1: test the 26 neighbours, queue the survivors' ranges
+  // squared conservative gaps to the neighbour slabs on each axis (index 0: minus side, 1: plus side)
+  float gx2[2], gy2[2], gz2[2];
+  {
+    const float fxl = g.ox + (float)cx * g.cell, fyl = g.oy + (float)cy * g.cell, fzl = g.oz + (float)cz * g.cell;
+    float t;
+    t = fmaxf(qx - fxl - g.slack, 0.0f);            gx2[0] = fmul(t, t);
+    t = fmaxf(fxl + g.cell - qx - g.slack, 0.0f);   gx2[1] = fmul(t, t);
+    t = fmaxf(qy - fyl - g.slack, 0.0f);            gy2[0] = fmul(t, t);
+    t = fmaxf(fyl + g.cell - qy - g.slack, 0.0f);   gy2[1] = fmul(t, t);
+    t = fmaxf(qz - fzl - g.slack, 0.0f);            gz2[0] = fmul(t, t);
+    t = fmaxf(fzl + g.cell - qz - g.slack, 0.0f);   gz2[1] = fmul(t, t);
+  }
+  const int tid = threadIdx.x;
+  int nlist = 0;
+  // (rows are a real loop, not unrolled: the kernel is instruction-fetch sensitive)
+#pragma unroll 1
+  for (int row = 0; row < 9; ++row) {
+    const int dz = row / 3 - 1, dy = row % 3 - 1;
+    {
+      const int z = cz + dz;
+      if (z < 0 || z >= g.nz) continue;
+    }
+    const float lz2 = dz == 0 ? 0.0f : (dz > 0 ? gz2[1] : gz2[0]);
+    if (lz2 > thr) continue;
+    {
+      const int y = cy + dy;
+      if (y < 0 || y >= g.ny) continue;
+      const float ly2 = dy == 0 ? 0.0f : (dy > 0 ? gy2[1] : gy2[0]);
+      const float lyz = fadd(ly2, lz2);  // (0 + ly2) + lz2 <= (dx2 + dy2) + dz2
+      if (lyz > thr) continue;
+      const int* cs = cs_own + (dz * g.ny + dy) * g.nx;
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        if (dx == 0 && dy == 0 && dz == 0) continue;
+        const int x = cx + dx;
+        if (x < 0 || x >= g.nx) continue;
+        const float lx2 = dx == 0 ? 0.0f : gx2[dx > 0];
+        const float lb = fadd(fadd(lx2, ly2), lz2);
+        if (lb > thr) continue;
+        const int s = __ldg(cs + dx), e = __ldg(cs + dx + 1);
+        const int cnt = e - s;
+        if (cnt <= 0) continue;
+        if (nlist < kListCap && cnt <= 0xFFFF) {
+          sc.start[nlist][tid] = s;
+          sc.meta[nlist][tid] = (__float_as_uint(lb) & 0xFFFF0000u) | (unsigned)cnt;
+          ++nlist;
+        } else {  // list full (no seed yet / very sparse own cell): scan now
+          scan_range(g.pts, s, e, qx, qy, qz, r.key, r.pos);
+          thr = fminf(bound2, key_d2(r.key));
+        }
+      }
+    }
   }
 
-  // ---- 3x3x3 block: centre row, then the 4 edge-adjacent rows, then the 4 corner rows; inside a
-  // row the three cells are pruned one by one against thr
+  // ---- phase 2: one flattened loop over the queued ranges
   {
-    // conservative x-gaps to the left / right neighbour cells (0 for the own cell)
-    const float gxl = fmaxf(qx - (g.ox + (float)cx * g.cell) - g.slack, 0.0f);
-    const float gxr = fmaxf((g.ox + (float)(cx + 1) * g.cell) - qx - g.slack, 0.0f);
-    const float gxl2 = fmul(gxl, gxl), gxr2 = fmul(gxr, gxr);
-    const bool has_l = cx > 0, has_r = cx < g.nx - 1;
-#pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const int dy = (t == 1 || t == 5 || t == 7) ? -1 : ((t == 2 || t == 6 || t == 8) ? 1 : 0);
-      const int dz = (t == 3 || t == 5 || t == 6) ? -1 : ((t == 4 || t == 7 || t == 8) ? 1 : 0);
-      const int y = cy + dy, z = cz + dz;
-      if (y < 0 || y >= g.ny || z < 0 || z >= g.nz) continue;
-      const float ly = slab_gap(qy, g.oy, g.cell, y, y, g.slack);
-      const float lz = slab_gap(qz, g.oz, g.cell, z, z, g.slack);
-      const float ly2 = fmul(ly, ly), lz2 = fmul(lz, lz);
-      const float lb = fadd(ly2, lz2);
-      if (lb > thr) continue;
-      const int* cs = g.cell_start + (z * g.ny + y) * g.nx + cx;
-      const int s0 = __ldg(cs), s1 = __ldg(cs + 1);
-      scan_range(g.pts, s0, s1, qx, qy, qz, r.key, r.pos);
-      thr = fminf(bound2, key_d2(r.key));
-      if (has_l && !(fadd(fadd(gxl2, ly2), lz2) > thr)) {
-        scan_range(g.pts, __ldg(cs - 1), s0, qx, qy, qz, r.key, r.pos);
-        thr = fminf(bound2, key_d2(r.key));
+    int li = 0, j = 0, e = 0;
+    for (;;) {
+      if (j >= e) {
+        if (li >= nlist) break;
+        const int s = sc.start[li][tid];
+        const unsigned m = sc.meta[li][tid];
+        ++li;
+        if (__uint_as_float(m & 0xFFFF0000u) > thr) continue;  // thr has tightened since phase 1
+        j = s;
+        e = s + (int)(m & 0xFFFFu);
       }
-      if (has_r && !(fadd(fadd(gxr2, ly2), lz2) > thr)) {
-        scan_range(g.pts, s1, __ldg(cs + 2), qx, qy, qz, r.key, r.pos);
-        thr = fminf(bound2, key_d2(r.key));
+      const float4 p = __ldg(g.pts + j);
+      const float d = sqdist3(qx, qy, qz, p.x, p.y, p.z);
+      const unsigned long long k = pack_key(d, __float_as_int(p.w));
+      if (k < r.key) {
+        r.key = k;
+        r.pos = j;
+        thr = fminf(bound2, d);
       }
+      ++j;
     }
   }
 
@@ -159,10 +225,11 @@ __global__ void __launch_bounds__(kSweepThreads) nn_search_kernel(GridView g, co
                                                                   int* __restrict__ idx, float* __restrict__ d2,
                                                                   int* __restrict__ unresolved_list,
                                                                   unsigned int* __restrict__ unresolved_count) {
+  __shared__ NNScratch<kSweepThreads> sc;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float4 p = __ldg(q + i);
-  NNResult r = grid_nn(g, p.x, p.y, p.z, bound2, max_rings);
+  NNResult r = grid_nn<kSweepThreads>(g, p.x, p.y, p.z, bound2, max_rings, -1, sc);
   if (!r.resolved) {
     unsigned int slot = atomicAdd(unresolved_count, 1u);
     unresolved_list[slot] = i;

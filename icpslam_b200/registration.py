@@ -104,7 +104,8 @@ def load_library() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
+    # B2ICP_LIB selects another build of the SAME sources (kernel tuning variants under lib/variants/)
+    path = os.environ.get("B2ICP_LIB") or _build.LIB_PATH
     if not os.path.exists(path):
         raise ImportError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(the CUDA extension is the only compute path)")
