@@ -17,6 +17,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -119,6 +120,7 @@ struct b2icp_handle {
   std::vector<cudaEvent_t> events;
   b2icp_timing timing;
   long long launches = 0;
+  int qpt_override = 0;  // B2ICP_QPT environment variable (tuning only)
 };
 
 namespace {
@@ -396,10 +398,20 @@ int run_batch(b2icp_handle* h, int B, const float* guesses) {
     }
     CK(cudaEventRecord(h->events[0], h->stream));
   }
-  dim3 grid((unsigned)((max_n + kSweepThreads - 1) / kSweepThreads), (unsigned)B, 1);
+  // queries per thread: amortise prologue / reduction / barrier when there is enough work to keep
+  // every SM's resident CTA slots full for at least two waves
+  auto ctas_at = [&](int qpt) { return (long long)B * (long long)((max_n + (size_t)kSweepThreads * qpt - 1) / ((size_t)kSweepThreads * qpt)); };
+  const long long want = 2LL * 148 * kSweepMinCtas;
+  const int qpt = h->qpt_override > 0 ? h->qpt_override : (ctas_at(4) >= want ? 4 : (ctas_at(2) >= want ? 2 : 1));
+  dim3 grid((unsigned)((max_n + (size_t)kSweepThreads * qpt - 1) / ((size_t)kSweepThreads * qpt)), (unsigned)B, 1);
   for (int it = 0; it < iters; ++it) {
     if (prof) CK(cudaEventRecord(h->events[2 + 2 * it], h->stream));
-    icp_sweep_p2p<<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>(), h->cfg);
+    if (qpt == 4)
+      icp_sweep_p2p<4><<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>(), h->cfg);
+    else if (qpt == 2)
+      icp_sweep_p2p<2><<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>(), h->cfg);
+    else
+      icp_sweep_p2p<1><<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>(), h->cfg);
     if (prof) CK(cudaEventRecord(h->events[3 + 2 * it], h->stream));
   }
   h->launches += iters;
@@ -609,6 +621,7 @@ int b2icp_create(const b2icp_params* p, b2icp_handle** out) {
   h->device = p->device;
   std::memset(&h->timing, 0, sizeof(h->timing));
   derive_config(h);
+  if (const char* e = getenv("B2ICP_QPT")) h->qpt_override = atoi(e);
   slot(h, 0);
   gslot(h, 0);
   bool ok = cudaSetDevice(h->device) == cudaSuccess &&

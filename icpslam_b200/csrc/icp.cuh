@@ -65,13 +65,17 @@ __device__ __forceinline__ bool grid_reduce_last(const ScanTask& t, double (*sme
   return true;
 }
 
+// QPT = queries per thread: consecutive 256-point slabs handled by the same CTA, so that the prologue,
+// the 17-value fp64 reduction and the CTA barrier are paid once per QPT queries (batches use 4; a
+// single scan uses 1 to keep every SM busy).
+template <int QPT>
 __global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) icp_sweep_p2p(const ScanTask* __restrict__ tasks, IcpConfig cfg) {
   __shared__ double smem[kSweepThreads / 32][kNumSums];
   __shared__ NNScratch<kSweepThreads> sc;
   __shared__ float sT[16];
   __shared__ int s_flags[2];
   const ScanTask& t = tasks[blockIdx.y];
-  const int ncta = (t.n + kSweepThreads - 1) / kSweepThreads;
+  const int ncta = (t.n + kSweepThreads * QPT - 1) / (kSweepThreads * QPT);
   if ((int)blockIdx.x >= ncta) return;
   IcpState* st = t.state;
   if (threadIdx.x < 16) sT[threadIdx.x] = st->Tinc[threadIdx.x];
@@ -85,8 +89,10 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) icp_sweep_p2p(co
 #pragma unroll
   for (int c = 0; c < kNumSums; ++c) acc[c] = 0.0;
 
-  const int i = blockIdx.x * kSweepThreads + threadIdx.x;
-  if (i < t.n) {
+#pragma unroll 1
+  for (int qi = 0; qi < QPT; ++qi) {
+    const int i = (blockIdx.x * QPT + qi) * kSweepThreads + threadIdx.x;
+    if (i >= t.n) break;
     const float4 p = first ? __ldg(t.src + i) : t.cur[i];
     const float4 q = xform_f(sT, p.x, p.y, p.z);
     t.cur[i] = q;
@@ -105,13 +111,13 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) icp_sweep_p2p(co
     if (keep) {
       const float4 m = __ldg(t.grid.pts + r.pos);
       const double sx = q.x, sy = q.y, sz = q.z, dx = m.x, dy = m.y, dz = m.z;
-      acc[0] = 1.0;
-      acc[1] = sx; acc[2] = sy; acc[3] = sz;
-      acc[4] = dx; acc[5] = dy; acc[6] = dz;
-      acc[7] = dx * sx; acc[8] = dx * sy; acc[9] = dx * sz;
-      acc[10] = dy * sx; acc[11] = dy * sy; acc[12] = dy * sz;
-      acc[13] = dz * sx; acc[14] = dz * sy; acc[15] = dz * sz;
-      acc[16] = (double)d2;
+      acc[0] += 1.0;
+      acc[1] += sx; acc[2] += sy; acc[3] += sz;
+      acc[4] += dx; acc[5] += dy; acc[6] += dz;
+      acc[7] += dx * sx; acc[8] += dx * sy; acc[9] += dx * sz;
+      acc[10] += dy * sx; acc[11] += dy * sy; acc[12] += dy * sz;
+      acc[13] += dz * sx; acc[14] += dz * sy; acc[15] += dz * sz;
+      acc[16] += (double)d2;
     }
   }
   cta_reduce_sums(acc, smem);
