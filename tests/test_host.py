@@ -1,0 +1,105 @@
+"""CPU tests of the host-side logic above the C ABI: Pose6DOF mirror, scan sharding, the per-batch
+gather (world_size 2 over gloo) and the shims' compile check."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from icpslam_b200 import pose6dof, replay, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_pose6dof_mirror_equals_oracle(oracle):
+    rng = np.random.default_rng(5)
+    for _ in range(20):
+        Ta, Tb = synth.random_rigid(rng, 5, 3), synth.random_rigid(rng, 5, 3)
+        a, b = pose6dof.from_matrix(Ta), pose6dof.from_matrix(Tb)
+        assert np.abs(a - oracle.pose_from_matrix(Ta)).max() < 1e-14
+        assert np.abs(pose6dof.compose(a, b) - oracle.pose_compose(a, b)).max() < 1e-14
+        assert np.abs(pose6dof.inverse(a) - oracle.pose_inverse(a)).max() < 1e-14
+        assert np.abs(pose6dof.to_matrix(pose6dof.compose(a, b)) - Ta @ Tb).max() < 1e-12
+
+
+def test_shard_range_partitions_exactly():
+    for n in (0, 1, 7, 511, 512):
+        for world in (1, 2, 3, 4, 8):
+            blocks = [replay.shard_range(n, world, r) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in blocks]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_compose_odometry_skips_rejected_scans():
+    T = np.eye(4)
+    T[0, 3] = 1.0
+    recs = np.zeros((3, replay.RECORD))
+    recs[:, :16] = T.reshape(-1)
+    recs[:, 16] = [1, 0, 1]                      # scan 1 did not converge: dropped, pose kept
+    poses = replay.compose_odometry(recs)
+    assert poses[:, 0].tolist() == [0, 1, 1, 2]
+    poses = replay.compose_odometry(recs, fitness=[0.1, 0.1, 25.0])   # fitness >= 20 rejected
+    assert poses[:, 0].tolist() == [0, 1, 1, 1]
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_total = 7
+    lo, hi = replay.shard_range(n_total, world, rank)
+    local = np.zeros((hi - lo, replay.RECORD))
+    for i in range(lo, hi):
+        T = np.eye(4)
+        T[0, 3] = i + 1
+        local[i - lo, :16] = T.reshape(-1)
+        local[i - lo, 16:] = (1, 5 + i, 100 + i, 0.5)
+    table = replay.gather_records(local, n_total)
+    poses = replay.compose_odometry(table)
+    q.put((rank, table[:, 3].tolist(), table[:, 17].tolist(), poses[-1, 0]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_of_transforms_world2_gloo():
+    """The only exchange step of the path: per-scan records to every rank, in scan order."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, tx, iters, last_x in got:
+        assert tx == [1, 2, 3, 4, 5, 6, 7]
+        assert iters == [5, 6, 7, 8, 9, 10, 11]
+        assert last_x == sum(range(1, 8))
+
+
+def test_shims_compile_and_pose_selfcheck(b2lib, tmp_path):
+    """The C++ shims (IcpOdometer / OctreeMapper / Pose6DOF) build against include/b2icp.h and link to
+    libb2icp.so; their Pose6DOF algebra needs no GPU and is checked here."""
+    from icpslam_b200 import build as B
+    exe = str(tmp_path / "shim_driver")
+    cmd = ["/usr/bin/g++", "-O1", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "cpp", "shim_driver.cpp"),
+           "-L", B.LIB_DIR, "-lb2icp", f"-Wl,-rpath,{B.LIB_DIR}"]
+    subprocess.run(cmd, check=True)
+    out = subprocess.run([exe, "pose"], check=True, capture_output=True, text=True).stdout
+    import json
+    j = json.loads(out)
+    T = np.array([[0, -1, 0, 1], [1, 0, 0, 2], [0, 0, 1, 3], [0, 0, 0, 1.0]])
+    assert np.abs(np.array(j["a"]) - pose6dof.from_matrix(T)).max() < 1e-15
+    assert np.abs(np.array(j["ab"]) - pose6dof.compose(pose6dof.from_matrix(T), pose6dof.from_matrix(T))).max() < 1e-15
+    assert np.abs(np.array(j["ident"]) - pose6dof.identity()).max() < 1e-15
+    import torch
+    if not torch.cuda.is_available():             # no CPU fallback behind the shims either
+        r = subprocess.run([exe, "odom", "0.2", "/dev/null", "/dev/null"], capture_output=True, text=True)
+        assert r.returncode == 3 and "CUDA" in r.stderr

@@ -1,0 +1,187 @@
+"""CPU tests of the oracle (test infrastructure): committed golden vectors, independent witnesses
+(scipy cKDTree, numpy SVD / eigh, brute force) and analytic known-answer tests.
+PARITY UNPINNED: nothing here is an output of PCL; see oracle/b2icp_oracle.h."""
+import hashlib
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+from scipy.spatial import cKDTree
+
+from icpslam_b200 import synth
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "oracle_golden.json")))
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_golden_nn_integer_fixture(oracle):
+    tgt = synth.integer_cloud(11 + 4096, 4096)
+    q = synth.integer_cloud(12 + 4096, 4096, unique=False)
+    idx, d2 = oracle.KdTree(tgt).nn(q)
+    assert sha(idx) == GOLD["nn_integer_4096"]["idx_sha256"]
+    assert sha(d2) == GOLD["nn_integer_4096"]["d2_sha256"]
+    assert idx[:16].tolist() == GOLD["nn_integer_4096"]["idx_head"]
+    bi, bd = oracle.nn_brute(tgt, q)
+    assert np.array_equal(bi, idx) and np.array_equal(bd, d2)
+
+
+def test_golden_tie_heavy_lattice(oracle):
+    tgt = synth.integer_cloud(3, 3000, -8, 8)
+    q = synth.integer_cloud(4, 20000, -10, 10, unique=False)
+    idx, d2 = oracle.KdTree(tgt).nn(q)
+    assert sha(idx) == GOLD["nn_lattice_ties"]["idx_sha256"]
+    assert sha(d2) == GOLD["nn_lattice_ties"]["d2_sha256"]
+    # canonical tie rule: among equal d2 the smallest index (checked against an independent numpy scan)
+    for i in range(0, 200):
+        d = ((tgt[:, :3].astype(np.float64) - q[i, :3]) ** 2).sum(1)
+        assert idx[i] == int(np.flatnonzero(d == d.min())[0])
+
+
+def test_kdtree_matches_scipy_on_real_valued_clouds(oracle):
+    _, _, sw = synth.sweep_sequence(1, 2, n_beams=64, n_az=256)
+    idx, d2 = oracle.KdTree(sw[0]).nn(sw[1])
+    dd, ii = cKDTree(sw[0][:, :3].astype(np.float64)).query(sw[1][:, :3].astype(np.float64))
+    assert (ii == idx).mean() > 0.9999            # float32 vs float64 distances may flip exact ties
+    assert np.abs(dd ** 2 - d2).max() < 1e-4
+    k_idx, k_d2 = oracle.KdTree(sw[0]).knn(sw[1][:500], 20)
+    dd, ii = cKDTree(sw[0][:, :3].astype(np.float64)).query(sw[1][:500, :3].astype(np.float64), k=20)
+    assert (ii == k_idx).mean() > 0.999
+    assert (np.diff(k_d2, axis=1) >= 0).all()     # sorted=true
+
+
+def test_knn_edge_cases(oracle):
+    pts = synth.as_xyzw(np.random.default_rng(0).uniform(-1, 1, (10, 3)))
+    with pytest.raises(RuntimeError):
+        oracle.KdTree(pts).knn(pts, 20)           # k > N: PCL's computeCovariances bails out
+    idx, d2 = oracle.KdTree(pts).knn(pts, 10)
+    assert (idx[:, 0] == np.arange(10)).all() and (d2[:, 0] == 0).all()
+    dup = np.concatenate([pts, pts])
+    idx, _ = oracle.KdTree(dup).nn(pts)
+    assert (idx == np.arange(10)).all()           # duplicates: smallest index
+
+
+def test_svd3_and_umeyama_kats(oracle):
+    rng = np.random.default_rng(1)
+    for _ in range(20):
+        A = rng.normal(size=(3, 3))
+        U, s, V = oracle.svd3(A)
+        assert np.abs(U @ np.diag(s) @ V.T - A).max() < 1e-13
+        assert np.abs(s - np.linalg.svd(A)[1]).max() < 1e-13
+        assert np.abs(U.T @ U - np.eye(3)).max() < 1e-13 and np.abs(V.T @ V - np.eye(3)).max() < 1e-13
+    A = np.outer([1, 2, 3], [4, 5, 6.0])          # rank 1
+    U, s, V = oracle.svd3(A)
+    assert np.abs(U @ np.diag(s) @ V.T - A).max() < 1e-12 and abs(abs(np.linalg.det(U)) - 1) < 1e-12
+    # exact rigid motion, generic cloud
+    P = synth.as_xyzw(rng.uniform(-5, 5, (500, 3)))
+    T = synth.random_rigid(rng, 2.0, 1.0)
+    Q = synth.as_xyzw(P[:, :3].astype(np.float64) @ T[:3, :3].T + T[:3, 3])
+    assert np.abs(oracle.umeyama(P, Q) - T).max() < 1e-5
+    # planar z = 0 cloud (rank-2 covariance): rotation about z recovered, no reflection
+    P2 = P.copy()
+    P2[:, 2] = 0
+    Tz = np.eye(4)
+    Tz[:3, :3] = synth.rot_xyz(0, 0, 0.3)
+    Tz[:3, 3] = (0.5, -0.2, 0)
+    Q2 = synth.as_xyzw(P2[:, :3].astype(np.float64) @ Tz[:3, :3].T + Tz[:3, 3])
+    Tu = oracle.umeyama(P2, Q2)
+    assert np.abs(Tu - Tz).max() < 1e-5 and np.linalg.det(Tu[:3, :3]) > 0.999
+    # reflection trap: a mirrored cloud must still give a proper rotation (det(U) det(V) < 0 branch)
+    Qm = Q.copy()
+    Qm[:, 0] *= -1
+    assert np.linalg.det(oracle.umeyama(P, Qm)[:3, :3]) > 0.999
+
+
+def test_transform_cloud_semantics(oracle):
+    rng = np.random.default_rng(2)
+    cloud = synth.as_xyzw(rng.uniform(-80, 80, (1000, 3)))
+    T = synth.random_rigid(rng, 3.0, 0.7)
+    outd = oracle.transform_cloud(cloud, T, True)
+    ref = (cloud[:, :3].astype(np.float64) @ T[:3, :3].T + T[:3, 3]).astype(np.float32)
+    assert np.abs(outd[:, :3] - ref).max() <= 8e-6 and (outd[:, 3] == 1).all()
+    outf = oracle.transform_cloud(cloud, T, False)
+    assert np.abs(outf[:, :3] - ref).max() <= 3e-5
+    Tf = T.astype(np.float32)                      # ((m0 x + m1 y) + m2 z) + m3 in float32
+    x, y, z = cloud[:, 0], cloud[:, 1], cloud[:, 2]
+    exp = ((Tf[0, 0] * x + Tf[0, 1] * y) + Tf[0, 2] * z) + Tf[0, 3]
+    assert np.array_equal(outf[:, 0], exp.astype(np.float32))
+
+
+def test_golden_p2p_and_kats(oracle):
+    _, _, sw = synth.sweep_sequence(1, 2, n_beams=64, n_az=64)
+    assert sha(sw[0]) == GOLD["c1_p2p"]["cloud_sha256"]          # the generator itself is pinned
+    r = oracle.align(oracle.default_params("odometer"), sw[1], sw[0], record_iter=-1)
+    assert r["iterations"] == GOLD["c1_p2p"]["iterations"] and r["n_corr"] == GOLD["c1_p2p"]["n_corr"]
+    assert np.abs(r["T"] - np.array(GOLD["c1_p2p"]["T"])).max() < 1e-6
+    assert sha(r["corr_idx"]) == GOLD["c1_p2p"]["corr_idx_sha256"]
+    _, _, sc = synth.planar_stream(3, 2)
+    r = oracle.align(oracle.default_params("odometer"), sc[1], sc[0])
+    assert r["iterations"] == GOLD["c3_planar_p2p"]["iterations"]
+    assert np.abs(r["T"] - np.array(GOLD["c3_planar_p2p"]["T"])).max() < 1e-6
+    # analytic: Q = T P, same order, no noise
+    rng = np.random.default_rng(0)
+    P = synth.as_xyzw(rng.uniform(-5, 5, (2000, 3)))
+    T = synth.random_rigid(rng, 0.05, 0.01)
+    Q = oracle.transform_cloud(P, T)
+    r = oracle.align(oracle.default_params("mapper"), P, Q)
+    assert r["converged"] and np.abs(r["T"] - T).max() < 5e-6
+    r = oracle.align(oracle.default_params("mapper"), P, P)
+    assert r["iterations"] <= 2 and np.abs(r["T"] - np.eye(4)).max() < 1e-7
+    # PCL semantics: fewer than 3 correspondences -> converged_ = false
+    far = P.copy()
+    far[:, :3] += 100
+    r = oracle.align(oracle.default_params("odometer"), far, P)
+    assert r["rc"] == -4 and not r["converged"]
+    assert oracle.align(oracle.default_params("odometer"), P[:0], P)["rc"] == -2
+    fit = oracle.fitness(P, Q, T.astype(np.float32))
+    assert fit < 1e-9
+
+
+def test_gicp_covariances_and_golden(oracle):
+    rng = np.random.default_rng(3)
+    patch = synth.as_xyzw(np.c_[rng.uniform(-1, 1, (400, 2)), 1e-3 * rng.normal(size=400)])
+    C = oracle.covariances(patch)
+    w, v = np.linalg.eigh(C[0])
+    assert np.allclose(w, [1e-3, 1, 1], atol=1e-9) and abs(abs(v[2, 0]) - 1) < 1e-3   # normal = z
+    _, _, sw = synth.sweep_sequence(1, 2, n_beams=64, n_az=64)
+    C = oracle.covariances(sw[0][:512])
+    assert abs(np.trace(C, axis1=1, axis2=2).sum() - GOLD["cov_512"]["trace_sum"]) < 1e-6
+    assert np.abs(C[0] - np.array(GOLD["cov_512"]["first"])).max() < 1e-9
+    # independent witness: neighbourhood covariance via numpy, same regularisation
+    idx, _ = oracle.KdTree(sw[0][:512]).knn(sw[0][:8], 20)
+    for i in range(8):
+        nb = sw[0][:512][idx[i], :3].astype(np.float64)
+        w, v = np.linalg.eigh(np.cov(nb.T, bias=True))
+        n = v[:, 0]
+        assert np.abs(C[i] - (np.eye(3) - (1 - 1e-3) * np.outer(n, n))).max() < 2e-3
+    r = oracle.align(oracle.default_params("odometer", oracle.MODE_GICP_BFGS), sw[1], sw[0])
+    assert r["rc"] == 0 and r["iterations"] == GOLD["c1_gicp"]["iterations"]
+    assert np.abs(r["T"] - np.array(GOLD["c1_gicp"]["T"])).max() < 1e-6
+    # analytic KAT for the whole GICP loop
+    P = synth.as_xyzw(rng.uniform(-5, 5, (3000, 3)) * [1, 1, 0.2])
+    T = synth.random_rigid(rng, 0.05, 0.01)
+    Q = oracle.transform_cloud(P, T)
+    r = oracle.align(oracle.default_params("mapper", oracle.MODE_GICP_BFGS), P, Q)
+    assert r["rc"] == 0 and np.abs(r["T"] - T).max() < 2e-5
+    with pytest.raises(RuntimeError):
+        oracle.covariances(P[:10])               # N < k_correspondences
+
+
+def test_pose_algebra_matches_reference_formulas(oracle):
+    from scipy.spatial.transform import Rotation as Rot
+    rng = np.random.default_rng(4)
+    for _ in range(20):
+        Ta, Tb = synth.random_rigid(rng, 5, 3), synth.random_rigid(rng, 5, 3)
+        a, b = oracle.pose_from_matrix(Ta), oracle.pose_from_matrix(Tb)
+        qa = Rot.from_matrix(Ta[:3, :3]).as_quat()                 # x,y,z,w
+        assert min(np.abs(a[3:] - qa[[3, 0, 1, 2]]).max(), np.abs(a[3:] + qa[[3, 0, 1, 2]]).max()) < 1e-12
+        c = oracle.pose_compose(a, b)
+        Tc = Ta @ Tb
+        assert np.abs(c[:3] - Tc[:3, 3]).max() < 1e-12
+        assert np.abs(Rot.from_quat(c[[4, 5, 6, 3]]).as_matrix() - Tc[:3, :3]).max() < 1e-12
+        i = oracle.pose_compose(a, oracle.pose_inverse(a))
+        assert np.abs(i[:3]).max() < 1e-12 and abs(abs(i[3]) - 1) < 1e-12
