@@ -147,6 +147,7 @@ struct Functor {
   const std::vector<double>* mahalanobis; /* 9 per source point */
   float base[16];                    /* base_transformation_ */
   int threads;
+  bool exact_double = false;
   long evals = 0;
 
   void fdf(const double* x, double* f, double* g) {
@@ -160,9 +161,24 @@ struct Functor {
     for (long i = 0; i < m; ++i) {
       const float* ps = src + 4 * (size_t)(*idx_src)[i];
       const float* pt = tgt + 4 * (size_t)(*idx_tgt)[i];
-      float pp[3];
-      xform_f(Tx, ps, pp);
-      double res[3] = {(double)(pp[0] - pt[0]), (double)(pp[1] - pt[1]), (double)(pp[2] - pt[2])};
+      double res[3];
+      if (!exact_double) {
+        float pp[3];
+        xform_f(Tx, ps, pp);
+        res[0] = (double)(pp[0] - pt[0]);
+        res[1] = (double)(pp[1] - pt[1]);
+        res[2] = (double)(pp[2] - pt[2]);
+      } else {
+        /* sensitivity experiment only (params.reserved[0] = 1): the same residual with a double
+         * rotation and double arithmetic — what a closed-form normal-equation evaluation would see */
+        const double cr = std::cos(x[3]), sr = std::sin(x[3]), cp = std::cos(x[4]), sp = std::sin(x[4]),
+                     cy = std::cos(x[5]), sy = std::sin(x[5]);
+        const double Rd[9] = {cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr,
+                              sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr,
+                              -sp,     cp * sr,                cp * cr};
+        for (int r = 0; r < 3; ++r)
+          res[r] = Rd[3 * r] * ps[0] + Rd[3 * r + 1] * ps[1] + Rd[3 * r + 2] * ps[2] + x[r] - (double)pt[r];
+      }
       const double* M = &(*mahalanobis)[9 * (size_t)(*idx_src)[i]];
       double tmp[3] = {M[0] * res[0] + M[1] * res[1] + M[2] * res[2], M[3] * res[0] + M[4] * res[1] + M[5] * res[2],
                        M[6] * res[0] + M[7] * res[1] + M[8] * res[2]};
@@ -672,6 +688,7 @@ int b2o_align_gicp_impl(const b2icp_params* p, const float* src, size_t ns, cons
     fn.mahalanobis = &mahal;
     std::memcpy(fn.base, guess, sizeof(guess));
     fn.threads = threads;
+    fn.exact_double = p->reserved[0] == 1;
     BFGS bfgs;
     bfgs.fn = &fn;
     int inner = 0, result;
