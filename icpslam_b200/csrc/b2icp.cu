@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "gicp.cuh"
 #include "grid.cuh"
 #include "icp.cuh"
 #include "nn.cuh"
@@ -75,22 +76,26 @@ struct GridSlot {
   Cloud tgt;                     // owned copy of the target (unused when the grid borrows a slot's source)
   const float4* pts = nullptr;   // the cloud the grid indexes
   DeviceBuf sorted, cell_start, cell_of, rank, tile_sums, bbox;
+  DeviceBuf cov;                 // GICP: 9 doubles per point (original order), valid while the grid is
+  bool cov_valid = false;
   GridView view;
   double cell = 0, min_cell = 0;
   float mn[3], mx[3];
   double occupancy = 0;
   bool valid = false;
   void release() {
-    for (DeviceBuf* b : {&tgt.raw, &sorted, &cell_start, &cell_of, &rank, &tile_sums, &bbox}) b->release();
+    for (DeviceBuf* b : {&tgt.raw, &sorted, &cell_start, &cell_of, &rank, &tile_sums, &bbox, &cov}) b->release();
   }
 };
 
 struct ScanSlot {
   Cloud src;
   DeviceBuf cur, corr_idx, corr_d2, corr_pos, partials;
+  DeviceBuf cov, mahal, gicp_partials;  // GICP: source covariances, Mahalanobis matrices, per-CTA sums
   int grid = 0;
   void release() {
-    for (DeviceBuf* b : {&src.raw, &cur, &corr_idx, &corr_d2, &corr_pos, &partials}) b->release();
+    for (DeviceBuf* b : {&src.raw, &cur, &corr_idx, &corr_d2, &corr_pos, &partials, &cov, &mahal, &gicp_partials})
+      b->release();
   }
 };
 
@@ -121,6 +126,9 @@ struct b2icp_handle {
   b2icp_timing timing;
   long long launches = 0;
   int qpt_override = 0;  // B2ICP_QPT environment variable (tuning only)
+  double* h_gicp_partials = nullptr;  // pinned read-back of gicp_fdf_kernel's per-CTA sums
+  size_t h_gicp_partials_cap = 0;
+  long gicp_evals = 0;
 };
 
 namespace {
@@ -267,7 +275,10 @@ int grid_enqueue_build(b2icp_handle* h, GridSlot* g, size_t n_) {
 
 // Build `count` grids (bbox pass, sort, occupancy check with at most two refinements).
 int build_grids(b2icp_handle* h, GridSlot* const* g, const size_t* n, int count) {
-  for (int i = 0; i < count; ++i) g[i]->valid = false;
+  for (int i = 0; i < count; ++i) {
+    g[i]->valid = false;
+    g[i]->cov_valid = false;
+  }
   int rc = grids_bbox(h, g, n, count);
   if (rc) return rc;
   std::vector<int> todo(count);
@@ -491,10 +502,14 @@ int nn_search_impl(b2icp_handle* h, const float4* d_q, size_t n, int* d_idx, flo
   return B2ICP_OK;
 }
 
+#include "gicp_host.inl"
+
 int batch_impl(b2icp_handle* h, const float* const* src, const size_t* n_src, const float* const* tgt,
                const size_t* n_tgt, size_t batch, int with_fitness, b2icp_result* out, bool from_device) {
   for (size_t i = 0; i < batch; ++i) identity_result(&out[i]);
   if (batch == 0) return B2ICP_OK;
+  if (h->params.mode != B2ICP_MODE_P2P_SVD)
+    return fail(h, B2ICP_ERR_INVALID_ARG, "b2icp_align_batch runs the point-to-point mode only; use b2icp_align for GICP");
   const bool shared_target = (tgt == nullptr);
   if (shared_target && !gslot(h, 0).valid) return fail(h, B2ICP_ERR_NO_TARGET, "no target cloud set");
   if (!shared_target && !tgt[0] && !gslot(h, 0).valid) return fail(h, B2ICP_ERR_NO_TARGET, "pair 0 has no target");
@@ -654,6 +669,7 @@ int b2icp_destroy(b2icp_handle* h) {
   if (h->h_states) cudaFreeHost(h->h_states);
   if (h->h_tasks) cudaFreeHost(h->h_tasks);
   if (h->h_bbox) cudaFreeHost(h->h_bbox);
+  if (h->h_gicp_partials) cudaFreeHost(h->h_gicp_partials);
   if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
   return B2ICP_OK;
@@ -742,7 +758,8 @@ int b2icp_align(b2icp_handle* h, const float* guess, b2icp_result* out, float* a
   if (!s.src.valid) return fail(h, B2ICP_ERR_NO_SOURCE, "no source cloud set");
   if (!gslot(h, 0).valid) return fail(h, B2ICP_ERR_NO_TARGET, "no target cloud set");
   h->aligned = false;
-  int rc = run_batch(h, 1, guess);
+  const bool gicp = h->params.mode == B2ICP_MODE_GICP_BFGS;
+  int rc = gicp ? run_gicp(h, guess) : run_batch(h, 1, guess);
   if (rc) return rc;
   const size_t n = s.src.n;
   if (aligned_xyzw) {
@@ -752,8 +769,13 @@ int b2icp_align(b2icp_handle* h, const float* guess, b2icp_result* out, float* a
     h->launches += 1;
     CK(cudaMemcpyAsync(aligned_xyzw, h->xf_out.p, n * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
   }
-  rc = read_states(h, 1);
-  if (rc) return rc;
+  if (gicp) {  // run_gicp left the final state in h_states[0] and mirrored it to the device
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+  } else {
+    rc = read_states(h, 1);
+    if (rc) return rc;
+  }
   fill_result(h->h_states[0], out);
   h->aligned = true;
   if (h->h_states[0].status != 0) {
@@ -890,6 +912,25 @@ int b2icp_align_batch_device(b2icp_handle* h, const float* const* d_src, const s
   std::lock_guard<std::mutex> lk(h->mu);
   CK(cudaSetDevice(h->device));
   return batch_impl(h, d_src, n_src, d_tgt, n_tgt, batch, with_fitness, out, true);
+}
+
+int b2icp_compute_covariances(b2icp_handle* h, const float* xyzw, size_t n, double* cov9) {
+  if (!h || !cov9) return B2ICP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CK(cudaSetDevice(h->device));
+  GridSlot& g = gslot(h, kMaxBatch + 2);  // scratch grid: leaves the handle's target untouched
+  int rc = upload_cloud(h, g.tgt, xyzw, n, false);
+  if (rc) return rc;
+  g.pts = g.tgt.raw.as<float4>();
+  GridSlot* gp = &g;
+  rc = build_grids(h, &gp, &n, 1);
+  if (rc) return rc;
+  rc = compute_covariances(h, g, n, g.cov);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(cov9, g.cov.p, n * 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  return B2ICP_OK;
 }
 
 int b2icp_get_timing(b2icp_handle* h, b2icp_timing* out) {

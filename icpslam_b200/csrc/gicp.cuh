@@ -1,0 +1,409 @@
+// gicp.cuh — the device half of pcl::GeneralizedIterativeClosestPoint, the class the reference
+// instantiates (reference src/icpslam/icp_odometer.cpp:188, src/icpslam/octree_mapper.cpp:104;
+// SURVEY.md App. A.2):
+//   K5  knn_cov_kernel      computeCovariances: k nearest neighbours (k = 20, the point itself included),
+//                           double covariance from float products, 3x3 SVD, eigenvalues -> (1, 1, eps)
+//   G2  gicp_corr_kernel    per outer iteration: query = transformation_ * (guess * p) in float, exact
+//                           1-NN (nn.cuh), strict gate d2 < max^2, M = (R C1 R^T + C2)^-1
+//   G3  gicp_fdf_kernel     one evaluation of the BFGS cost functor (f, df in one pass): 13 sums
+// The BFGS recursion itself is O(1) scalar work and runs on the host (gicp_host.hpp).
+//
+// PCL's GICP does not survive a change in the last bit of f (its line search ends on a round-off
+// test), so everything here is written to be BIT-IDENTICAL to a fixed arithmetic definition:
+//   * every double operation is an explicit __dmul_rn / __dadd_rn / __dsub_rn / __ddiv_rn / __dsqrt_rn in
+//     the order of the C expression it restates (no FMA contraction, no reassociation);
+//   * neighbour sums run in (d2, index) order; cross-point sums use a fixed tree: 256-point CTAs, xor
+//     butterfly 16,8,4,2,1 inside each warp, the 8 warp sums added in order, CTA sums added in order on
+//     the host.
+#pragma once
+#include "common.cuh"
+#include "nn.cuh"
+
+namespace b2 {
+
+constexpr int kGicpThreads = 256;
+constexpr int kGicpSums = 14;  // f, g0..g2, R00..R22, count
+constexpr int kMaxK = 32;      // k_correspondences <= 32
+
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+
+// ---- 3x3 helpers, each a literal restatement of its C expression (left-to-right) -----------------
+// C = A * B :   t = A[3r]*B[c] + A[3r+1]*B[3+c] + A[3r+2]*B[6+c]
+__device__ __forceinline__ void mat3_mul(const double* A, const double* B, double* C) {
+  double t[9];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      t[3 * r + c] = dadd(dadd(dmul(A[3 * r], B[c]), dmul(A[3 * r + 1], B[3 + c])), dmul(A[3 * r + 2], B[6 + c]));
+#pragma unroll
+  for (int i = 0; i < 9; ++i) C[i] = t[i];
+}
+// C = A * B^T
+__device__ __forceinline__ void mat3_mul_bt(const double* A, const double* B, double* C) {
+  double t[9];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      t[3 * r + c] =
+          dadd(dadd(dmul(A[3 * r], B[3 * c]), dmul(A[3 * r + 1], B[3 * c + 1])), dmul(A[3 * r + 2], B[3 * c + 2]));
+#pragma unroll
+  for (int i = 0; i < 9; ++i) C[i] = t[i];
+}
+// Eigen's closed-form inverse: cofactors times 1/det
+__device__ __forceinline__ void mat3_inv(const double* M, double* I) {
+  const double c00 = dsub(dmul(M[4], M[8]), dmul(M[5], M[7]));
+  const double c01 = dsub(dmul(M[5], M[6]), dmul(M[3], M[8]));
+  const double c02 = dsub(dmul(M[3], M[7]), dmul(M[4], M[6]));
+  const double det = dadd(dadd(dmul(M[0], c00), dmul(M[1], c01)), dmul(M[2], c02));
+  const double id = ddiv(1.0, det);
+  I[0] = dmul(c00, id);
+  I[1] = dmul(dsub(dmul(M[2], M[7]), dmul(M[1], M[8])), id);
+  I[2] = dmul(dsub(dmul(M[1], M[5]), dmul(M[2], M[4])), id);
+  I[3] = dmul(c01, id);
+  I[4] = dmul(dsub(dmul(M[0], M[8]), dmul(M[2], M[6])), id);
+  I[5] = dmul(dsub(dmul(M[2], M[3]), dmul(M[0], M[5])), id);
+  I[6] = dmul(c02, id);
+  I[7] = dmul(dsub(dmul(M[1], M[6]), dmul(M[0], M[7])), id);
+  I[8] = dmul(dsub(dmul(M[0], M[4]), dmul(M[1], M[3])), id);
+}
+
+__device__ __forceinline__ void cross3r(const double* a, const double* b, double* c) {
+  c[0] = dsub(dmul(a[1], b[2]), dmul(a[2], b[1]));
+  c[1] = dsub(dmul(a[2], b[0]), dmul(a[0], b[2]));
+  c[2] = dsub(dmul(a[0], b[1]), dmul(a[1], b[0]));
+}
+__device__ __forceinline__ double norm3r(const double* a) {
+  return __dsqrt_rn(dadd(dadd(dmul(a[0], a[0]), dmul(a[1], a[1])), dmul(a[2], a[2])));
+}
+
+// U of the SVD A = U diag(s) V^T (s descending), by the fixed one-sided Jacobi recipe of the arithmetic
+// definition: pairs (0,1), (0,2), (1,2); rotate unless ga == 0 or |ga| <= 1e-17 sqrt(al be);
+// zeta = (be - al) / (2 ga); t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)); c = 1 / sqrt(1 + t^2); s = c t.
+__device__ void svd3_u(const double* A, double* U) {
+  double B[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) B[i] = A[i];
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    bool rotated = false;
+#pragma unroll
+    for (int pq = 0; pq < 3; ++pq) {
+      const int p = (pq == 2) ? 1 : 0;
+      const int q = (pq == 0) ? 1 : 2;
+      double al = 0, be = 0, ga = 0;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        al = dadd(al, dmul(B[3 * i + p], B[3 * i + p]));
+        be = dadd(be, dmul(B[3 * i + q], B[3 * i + q]));
+        ga = dadd(ga, dmul(B[3 * i + p], B[3 * i + q]));
+      }
+      if (ga == 0.0 || fabs(ga) <= dmul(1e-17, __dsqrt_rn(dmul(al, be)))) continue;
+      rotated = true;
+      const double zeta = ddiv(dsub(be, al), dmul(2.0, ga));
+      const double t = ddiv(zeta >= 0 ? 1.0 : -1.0, dadd(fabs(zeta), __dsqrt_rn(dadd(1.0, dmul(zeta, zeta)))));
+      const double c = ddiv(1.0, __dsqrt_rn(dadd(1.0, dmul(t, t))));
+      const double sn = dmul(c, t);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const double bp = B[3 * i + p], bq = B[3 * i + q];
+        B[3 * i + p] = dsub(dmul(c, bp), dmul(sn, bq));
+        B[3 * i + q] = dadd(dmul(sn, bp), dmul(c, bq));
+      }
+    }
+    if (!rotated) break;
+  }
+  double nrm[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+    nrm[j] = __dsqrt_rn(dadd(dadd(dmul(B[j], B[j]), dmul(B[3 + j], B[3 + j])), dmul(B[6 + j], B[6 + j])));
+  // stable descending order of the three columns
+  int o0 = 0, o1 = 1, o2 = 2;
+  if (nrm[o1] > nrm[o0]) { int t = o0; o0 = o1; o1 = t; }
+  if (nrm[o2] > nrm[o1]) { int t = o1; o1 = o2; o2 = t; }
+  if (nrm[o1] > nrm[o0]) { int t = o0; o0 = o1; o1 = t; }
+  const int ord[3] = {o0, o1, o2};
+  double s[3], u[3][3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) s[j] = nrm[ord[j]];
+  const double tiny = dadd(1e-300, dmul(s[0], 1e-14));
+  int rank = 0;
+  for (int j = 0; j < 3; ++j)
+    if (s[j] > tiny) {
+      const int c = ord[j];
+      for (int i = 0; i < 3; ++i) u[j][i] = ddiv(B[3 * i + c], s[j]);
+      rank = j + 1;
+    }
+  if (rank == 0) {
+    for (int j = 0; j < 3; ++j)
+      for (int i = 0; i < 3; ++i) u[j][i] = (i == j) ? 1.0 : 0.0;
+  } else if (rank == 1) {
+    double e[3] = {0, 0, 0};
+    int m = 0;
+    for (int i = 1; i < 3; ++i)
+      if (fabs(u[0][i]) < fabs(u[0][m])) m = i;
+    e[m] = 1.0;
+    cross3r(u[0], e, u[1]);
+    const double n1 = norm3r(u[1]);
+    for (int i = 0; i < 3; ++i) u[1][i] = ddiv(u[1][i], n1);
+    cross3r(u[0], u[1], u[2]);
+  } else if (rank == 2) {
+    cross3r(u[0], u[1], u[2]);
+    const double n2 = norm3r(u[2]);
+    for (int i = 0; i < 3; ++i) u[2][i] = ddiv(u[2][i], n2);
+  }
+  for (int j = 0; j < 3; ++j)
+    for (int i = 0; i < 3; ++i) U[3 * i + j] = u[j][i];
+}
+
+// ---- K5: k nearest neighbours + regularised covariance ---------------------------------------------
+// One thread per point of `cloud` (original order); `g` is the grid built over the same cloud.  The k best
+// (d2, index) keys are kept sorted in a per-thread array; rings of cells are visited until the distance to
+// the outside of the visited block exceeds the k-th best distance.  Points that exhaust `max_rings` are
+// queued for the exhaustive fallback (same arithmetic, every point scanned).
+__device__ __forceinline__ void knn_offer(unsigned long long* keys, int k, unsigned long long c) {
+  if (c >= keys[k - 1]) return;
+  int p = k - 1;
+  while (p > 0 && keys[p - 1] > c) {
+    keys[p] = keys[p - 1];
+    --p;
+  }
+  keys[p] = c;
+}
+
+__device__ __forceinline__ void knn_scan(const float4* __restrict__ pts, int s, int e, float qx, float qy, float qz,
+                                         unsigned long long* keys, int k) {
+  for (int j = s; j < e; ++j) {
+    const float4 p = __ldg(pts + j);
+    knn_offer(keys, k, pack_key(sqdist3(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w)));
+  }
+}
+
+__device__ __forceinline__ void cov_from_keys(const float4* __restrict__ cloud, const unsigned long long* keys, int k,
+                                              double eps, double* __restrict__ out9) {
+  double mean[3] = {0, 0, 0};
+  double c00 = 0, c10 = 0, c11 = 0, c20 = 0, c21 = 0, c22 = 0;
+  for (int j = 0; j < k; ++j) {
+    const float4 pt = __ldg(cloud + key_idx(keys[j]));
+    mean[0] = dadd(mean[0], (double)pt.x);
+    mean[1] = dadd(mean[1], (double)pt.y);
+    mean[2] = dadd(mean[2], (double)pt.z);
+    c00 = dadd(c00, (double)fmul(pt.x, pt.x));  // float product, double accumulation (PCL)
+    c10 = dadd(c10, (double)fmul(pt.y, pt.x));
+    c11 = dadd(c11, (double)fmul(pt.y, pt.y));
+    c20 = dadd(c20, (double)fmul(pt.z, pt.x));
+    c21 = dadd(c21, (double)fmul(pt.z, pt.y));
+    c22 = dadd(c22, (double)fmul(pt.z, pt.z));
+  }
+  const double kd = (double)k;
+  for (int d = 0; d < 3; ++d) mean[d] = ddiv(mean[d], kd);
+  double C[9];
+  C[0] = dsub(ddiv(c00, kd), dmul(mean[0], mean[0]));
+  C[3] = dsub(ddiv(c10, kd), dmul(mean[1], mean[0]));
+  C[4] = dsub(ddiv(c11, kd), dmul(mean[1], mean[1]));
+  C[6] = dsub(ddiv(c20, kd), dmul(mean[2], mean[0]));
+  C[7] = dsub(ddiv(c21, kd), dmul(mean[2], mean[1]));
+  C[8] = dsub(ddiv(c22, kd), dmul(mean[2], mean[2]));
+  C[1] = C[3];
+  C[2] = C[6];
+  C[5] = C[7];
+  double U[9];
+  svd3_u(C, U);
+  double o[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int col = 0; col < 3; ++col) {
+    const double v = col == 2 ? eps : 1.0;
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) o[3 * r + c] = dadd(o[3 * r + c], dmul(dmul(v, U[3 * r + col]), U[3 * c + col]));
+  }
+  for (int i = 0; i < 9; ++i) out9[i] = o[i];
+}
+
+__global__ void __launch_bounds__(128) knn_cov_kernel(GridView g, const float4* __restrict__ cloud, int n, int k,
+                                                      double eps, int max_rings, double* __restrict__ cov9,
+                                                      int* __restrict__ unresolved_list,
+                                                      unsigned int* __restrict__ unresolved_count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 q = __ldg(cloud + i);
+  unsigned long long keys[kMaxK];
+  for (int j = 0; j < kMaxK; ++j) keys[j] = kInfKey;
+  const int cx = cell_coord(q.x, g.ox, g.inv_cell, g.nx);
+  const int cy = cell_coord(q.y, g.oy, g.inv_cell, g.ny);
+  const int cz = cell_coord(q.z, g.oz, g.inv_cell, g.nz);
+  bool resolved = false;
+  for (int R = 0;; ++R) {
+    if (R > max_rings) break;
+    const float thr = key_d2(keys[k - 1]);
+    const int z0 = max(cz - R, 0), z1 = min(cz + R, g.nz - 1);
+    const int y0 = max(cy - R, 0), y1 = min(cy + R, g.ny - 1);
+    const int xa = max(cx - R, 0), xb = min(cx + R, g.nx - 1);
+    for (int z = z0; z <= z1; ++z) {
+      const float lz = slab_gap(q.z, g.oz, g.cell, z, z, g.slack);
+      const float lz2 = fmul(lz, lz);
+      if (lz2 > thr) continue;
+      const bool zface = (z == cz - R) || (z == cz + R);
+      for (int y = y0; y <= y1; ++y) {
+        const float ly = slab_gap(q.y, g.oy, g.cell, y, y, g.slack);
+        if (fadd(fmul(ly, ly), lz2) > key_d2(keys[k - 1])) continue;
+        const int row = (z * g.ny + y) * g.nx;
+        if (zface || y == cy - R || y == cy + R) {
+          knn_scan(g.pts, __ldg(g.cell_start + row + xa), __ldg(g.cell_start + row + xb + 1), q.x, q.y, q.z, keys, k);
+        } else {
+          if (cx - R >= 0)
+            knn_scan(g.pts, __ldg(g.cell_start + row + cx - R), __ldg(g.cell_start + row + cx - R + 1), q.x, q.y, q.z, keys, k);
+          if (R > 0 && cx + R <= g.nx - 1)
+            knn_scan(g.pts, __ldg(g.cell_start + row + cx + R), __ldg(g.cell_start + row + cx + R + 1), q.x, q.y, q.z, keys, k);
+        }
+      }
+    }
+    // can anything outside the block [c - R, c + R]^3 still enter the list?
+    float ex = INFINITY;
+    if (cx - R > 0) ex = fminf(ex, q.x - (g.ox + (float)(cx - R) * g.cell));
+    if (cx + R < g.nx - 1) ex = fminf(ex, (g.ox + (float)(cx + R + 1) * g.cell) - q.x);
+    if (cy - R > 0) ex = fminf(ex, q.y - (g.oy + (float)(cy - R) * g.cell));
+    if (cy + R < g.ny - 1) ex = fminf(ex, (g.oy + (float)(cy + R + 1) * g.cell) - q.y);
+    if (cz - R > 0) ex = fminf(ex, q.z - (g.oz + (float)(cz - R) * g.cell));
+    if (cz + R < g.nz - 1) ex = fminf(ex, (g.oz + (float)(cz + R + 1) * g.cell) - q.z);
+    if (ex == INFINITY) {
+      resolved = true;
+      break;
+    }
+    ex = fmaxf(ex - g.slack, 0.0f);
+    if (fmul(ex, ex) > key_d2(keys[k - 1])) {
+      resolved = true;
+      break;
+    }
+  }
+  if (!resolved) {
+    unresolved_list[atomicAdd(unresolved_count, 1u)] = i;
+    return;
+  }
+  cov_from_keys(cloud, keys, k, eps, cov9 + (size_t)9 * i);
+}
+
+// exhaustive fallback: one thread per queued point, every point of the cloud offered in sorted-array order
+__global__ void __launch_bounds__(128) knn_cov_fallback(GridView g, const float4* __restrict__ cloud, int k, double eps,
+                                                        const int* __restrict__ list,
+                                                        const unsigned int* __restrict__ count,
+                                                        double* __restrict__ cov9) {
+  const unsigned int total = *count;
+  for (unsigned int w = blockIdx.x * blockDim.x + threadIdx.x; w < total; w += gridDim.x * blockDim.x) {
+    const int i = list[w];
+    const float4 q = __ldg(cloud + i);
+    unsigned long long keys[kMaxK];
+    for (int j = 0; j < kMaxK; ++j) keys[j] = kInfKey;
+    knn_scan(g.pts, 0, g.n, q.x, q.y, q.z, keys, k);
+    cov_from_keys(cloud, keys, k, eps, cov9 + (size_t)9 * i);
+  }
+}
+
+// ---- G2: correspondences + Mahalanobis matrices of one outer iteration -------------------------------
+struct GicpIterArgs {
+  float guess[16];   // base_transformation_
+  float T[16];       // transformation_
+  double R[9];       // top-left 3x3 of double(transformation_) * double(guess)
+  double max2;       // corr_dist_threshold_^2, gate is STRICT <
+  float bound2;
+  int max_rings;
+  int use_seed;
+};
+
+__global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas)
+    gicp_corr_kernel(GridView g, const float4* __restrict__ src, int n, GicpIterArgs a,
+                     const double* __restrict__ cov_src, const double* __restrict__ cov_tgt,
+                     double* __restrict__ mahal, int* __restrict__ corr_idx, float* __restrict__ corr_d2,
+                     int* __restrict__ corr_pos) {
+  __shared__ NNScratch<kSweepThreads> sc;
+  const int i = blockIdx.x * kSweepThreads + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = __ldg(src + i);
+  const float4 q0 = xform_f(a.guess, p.x, p.y, p.z);
+  const float4 q = xform_f(a.T, q0.x, q0.y, q0.z);
+  NNResult r;
+  r.key = kInfKey;
+  r.pos = -1;
+  if (isfinite(q.x) && isfinite(q.y) && isfinite(q.z))
+    r = grid_nn<kSweepThreads>(g, q.x, q.y, q.z, a.bound2, a.max_rings, a.use_seed ? corr_pos[i] : -1, sc);
+  const float d2 = key_d2(r.key);
+  const bool keep = (r.key != kInfKey) && ((double)d2 < a.max2);
+  const int ti = key_idx(r.key);
+  corr_idx[i] = keep ? ti : -1;
+  corr_d2[i] = d2;
+  corr_pos[i] = r.pos;
+  if (!keep) return;
+  double C1[9], C2[9], M[9], temp[9];
+#pragma unroll
+  for (int e = 0; e < 9; ++e) {
+    C1[e] = cov_src[(size_t)9 * i + e];
+    C2[e] = cov_tgt[(size_t)9 * ti + e];
+  }
+  mat3_mul(a.R, C1, M);
+  mat3_mul_bt(M, a.R, temp);
+#pragma unroll
+  for (int e = 0; e < 9; ++e) temp[e] = dadd(temp[e], C2[e]);
+  mat3_inv(temp, M);
+#pragma unroll
+  for (int e = 0; e < 9; ++e) mahal[(size_t)9 * i + e] = M[e];
+}
+
+// ---- G3: one evaluation of the cost functor (OptimizationFunctorWithIndices::fdf) ---------------------
+struct GicpEvalArgs {
+  float Tx[16];    // base_transformation_ with applyState(x) applied (built on the host)
+  float base[16];  // base_transformation_
+};
+
+__global__ void __launch_bounds__(kGicpThreads) gicp_fdf_kernel(const float4* __restrict__ src,
+                                                                const float4* __restrict__ tgt, int n, GicpEvalArgs a,
+                                                                const int* __restrict__ corr_idx,
+                                                                const double* __restrict__ mahal,
+                                                                double* __restrict__ partials) {
+  __shared__ double smem[kGicpThreads / 32][kGicpSums];
+  const int i = blockIdx.x * kGicpThreads + threadIdx.x;
+  double v[kGicpSums];
+#pragma unroll
+  for (int c = 0; c < kGicpSums; ++c) v[c] = 0.0;
+  const int ti = i < n ? corr_idx[i] : -1;
+  if (ti >= 0) {
+    const float4 ps = __ldg(src + i);
+    const float4 pt = __ldg(tgt + ti);
+    const float4 pp = xform_f(a.Tx, ps.x, ps.y, ps.z);
+    const double r0 = (double)fsub(pp.x, pt.x), r1 = (double)fsub(pp.y, pt.y), r2 = (double)fsub(pp.z, pt.z);
+    const double* M = mahal + (size_t)9 * i;
+    const double t0 = dadd(dadd(dmul(M[0], r0), dmul(M[1], r1)), dmul(M[2], r2));
+    const double t1 = dadd(dadd(dmul(M[3], r0), dmul(M[4], r1)), dmul(M[5], r2));
+    const double t2 = dadd(dadd(dmul(M[6], r0), dmul(M[7], r1)), dmul(M[8], r2));
+    v[0] = dadd(dadd(dmul(r0, t0), dmul(r1, t1)), dmul(r2, t2));
+    v[1] = t0;
+    v[2] = t1;
+    v[3] = t2;
+    const float4 pb = xform_f(a.base, ps.x, ps.y, ps.z);
+    const double b0 = (double)pb.x, b1 = (double)pb.y, b2 = (double)pb.z;
+    v[4] = dmul(b0, t0); v[5] = dmul(b0, t1); v[6] = dmul(b0, t2);
+    v[7] = dmul(b1, t0); v[8] = dmul(b1, t1); v[9] = dmul(b1, t2);
+    v[10] = dmul(b2, t0); v[11] = dmul(b2, t1); v[12] = dmul(b2, t2);
+    v[13] = 1.0;
+  }
+  // the fixed tree: xor butterfly inside the warp, warp sums in order, CTA sums in order (host)
+#pragma unroll
+  for (int c = 0; c < kGicpSums; ++c) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[c] = dadd(v[c], __shfl_xor_sync(0xFFFFFFFFu, v[c], o));
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+#pragma unroll
+    for (int c = 0; c < kGicpSums; ++c) smem[warp][c] = v[c];
+  }
+  __syncthreads();
+  if (threadIdx.x < kGicpSums) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kGicpThreads / 32; ++w) s = dadd(s, smem[w][threadIdx.x]);
+    partials[(size_t)blockIdx.x * kGicpSums + threadIdx.x] = s;
+  }
+}
+
+}  // namespace b2

@@ -1,0 +1,607 @@
+// gicp_host.inl — host half of the GICP mode (included by b2icp.cu inside its anonymous namespace).
+//
+// pcl::GeneralizedIterativeClosestPoint::computeTransformation's outer loop and PCL's BFGS (a port of GSL
+// vector_bfgs2 + linear_minimize.c) are O(1) scalar work per step and run here
+// on the host in double precision with the C library's sin / cos / atan2 — the only per-point work, the
+// cost functor, is one launch of gicp_fdf_kernel per evaluation.  The scalar recursion is written
+// expression by expression in a fixed order because PCL's line search ends on a round-off test: the result
+// is only reproducible when f, df and every scalar step are bit-identical.
+
+struct GicpHostFunctor {
+  b2icp_handle* h;
+  ScanSlot* s;
+  GridSlot* g;
+  float base[16];
+  long evals = 0;
+  int rc = 0;
+  long m = 0;
+
+  // GICP::applyState: R = AngleAxisf(x5,Z) * AngleAxisf(x4,Y) * AngleAxisf(x3,X) (float quaternions)
+  static void apply_state(float* t, const double* x) {
+    float hz = 0.5f * (float)x[5], hy = 0.5f * (float)x[4], hx = 0.5f * (float)x[3];
+    float qz[4] = {std::cos(hz), 0.f, 0.f, std::sin(hz)};
+    float qy[4] = {std::cos(hy), 0.f, std::sin(hy), 0.f};
+    float qx[4] = {std::cos(hx), std::sin(hx), 0.f, 0.f};
+    auto qmul = [](const float* a, const float* b, float* o) {
+      float w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+      float xx = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+      float yy = a[0] * b[2] + a[2] * b[0] + a[3] * b[1] - a[1] * b[3];
+      float zz = a[0] * b[3] + a[3] * b[0] + a[1] * b[2] - a[2] * b[1];
+      o[0] = w;
+      o[1] = xx;
+      o[2] = yy;
+      o[3] = zz;
+    };
+    float qzy[4], q[4];
+    qmul(qz, qy, qzy);
+    qmul(qzy, qx, q);
+    const float tx = 2.f * q[1], ty = 2.f * q[2], tz = 2.f * q[3];
+    const float twx = tx * q[0], twy = ty * q[0], twz = tz * q[0];
+    const float txx = tx * q[1], txy = ty * q[1], txz = tz * q[1];
+    const float tyy = ty * q[2], tyz = tz * q[2], tzz = tz * q[3];
+    float R[9] = {1.f - (tyy + tzz), txy - twz, txz + twy, txy + twz, 1.f - (txx + tzz), tyz - twx,
+                  txz - twy,         tyz + twx, 1.f - (txx + tyy)};
+    float n[9];
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {
+        float sum = 0.f;
+        for (int k = 0; k < 3; ++k) sum += R[3 * r + k] * t[4 * k + c];
+        n[3 * r + c] = sum;
+      }
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) t[4 * r + c] = n[3 * r + c];
+    t[3] += (float)x[0];
+    t[7] += (float)x[1];
+    t[11] += (float)x[2];
+  }
+
+  // GICP::computeRDerivative
+  static void compute_r_derivative(const double* x, const double* R, double* g) {
+    double phi = x[3], theta = x[4], psi = x[5];
+    double cphi = std::cos(phi), sphi = std::sin(phi), ctheta = std::cos(theta), stheta = std::sin(theta),
+           cpsi = std::cos(psi), spsi = std::sin(psi);
+    double dphi[9] = {0., sphi * spsi + cphi * cpsi * stheta,  cphi * spsi - cpsi * sphi * stheta,
+                      0., -cpsi * sphi + cphi * spsi * stheta, -cphi * cpsi - sphi * spsi * stheta,
+                      0., cphi * ctheta,                       -ctheta * sphi};
+    double dtheta[9] = {-cpsi * stheta, cpsi * ctheta * sphi, cphi * cpsi * ctheta,
+                        -spsi * stheta, ctheta * sphi * spsi, cphi * ctheta * spsi,
+                        -ctheta,        -sphi * stheta,       -cphi * stheta};
+    double dpsi[9] = {-ctheta * spsi, -cphi * cpsi - sphi * spsi * stheta, cpsi * sphi - cphi * spsi * stheta,
+                      cpsi * ctheta,  -cphi * spsi + cpsi * sphi * stheta, sphi * spsi + cphi * cpsi * stheta,
+                      0.,             0.,                                  0.};
+    auto inner = [&](const double* A) {
+      double r = 0.;
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) r += A[3 * j + i] * R[3 * i + j];
+      return r;
+    };
+    g[3] = inner(dphi);
+    g[4] = inner(dtheta);
+    g[5] = inner(dpsi);
+  }
+
+  // one cost-functor evaluation: kernel + D2H of the per-CTA sums + the in-order host sum
+  void fdf(const double* x, double* f, double* g) {
+    ++evals;
+    if (rc) {
+      if (f) *f = 0;
+      if (g) for (int i = 0; i < 6; ++i) g[i] = 0;
+      return;
+    }
+    GicpEvalArgs a;
+    std::memcpy(a.Tx, base, sizeof(base));
+    std::memcpy(a.base, base, sizeof(base));
+    apply_state(a.Tx, x);
+    const int n = (int)s->src.n;
+    const int nblk = (n + kGicpThreads - 1) / kGicpThreads;
+    gicp_fdf_kernel<<<nblk, kGicpThreads, 0, h->stream>>>(s->src.raw.as<float4>(), g_tgt(), n, a, s->corr_idx.as<int>(),
+                                                          s->mahal.as<double>(), s->gicp_partials.as<double>());
+    h->launches += 1;
+    cudaError_t e = cudaMemcpyAsync(h->h_gicp_partials, s->gicp_partials.p, (size_t)nblk * kGicpSums * sizeof(double),
+                                    cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) {
+      rc = B2ICP_ERR_CUDA;
+      h->err = std::string("gicp_fdf_kernel: ") + cudaGetErrorString(e);
+      return;
+    }
+    double S[kGicpSums];
+    for (int k = 0; k < kGicpSums; ++k) {
+      double tot = 0.0;
+      for (int b = 0; b < nblk; ++b) tot += h->h_gicp_partials[(size_t)b * kGicpSums + k];
+      S[k] = tot;
+    }
+    m = (long)S[13];
+    const double md = (double)m;
+    if (f) *f = S[0] / md;
+    if (g) {
+      g[0] = S[1] * 2.0 / md;
+      g[1] = S[2] * 2.0 / md;
+      g[2] = S[3] * 2.0 / md;
+      double R[9];
+      for (int k = 0; k < 9; ++k) R[k] = S[4 + k] * (2.0 / md);
+      compute_r_derivative(x, R, g);
+    }
+  }
+  const float4* g_tgt() const { return g->pts; }
+};
+
+// PCL's BFGS<FunctorType> (GSL vector_bfgs2), N = 6
+struct GicpBFGS {
+  static constexpr int N = 6;
+  static constexpr double kStepSize = 1.0, kDblEps = 2.220446049250313e-16;
+  enum { kRunning = -1, kSuccess = 0, kNoProgress = 1 };
+  GicpHostFunctor* fn;
+  double rho = 0.01, sigma = 0.01, tau1 = 9, tau2 = 0.05, tau3 = 0.5;
+  int order = 3;
+  double f = 0, g0norm = 0, pnorm = 0, fp0 = 0, delta_f = 0;
+  double gradient[N], x0[N], g0[N], p[N], dx[N];
+  double x_alpha[N], g_alpha[N], f_alpha = 0, df_alpha = 0;
+  double f_cache_key = 0, df_cache_key = 0, x_cache_key = 0, g_cache_key = 0;
+
+  static double dot(const double* a, const double* b) {
+    double s = 0;
+    for (int i = 0; i < N; ++i) s += a[i] * b[i];
+    return s;
+  }
+  static double norm(const double* a) { return std::sqrt(dot(a, a)); }
+  double slope() const { return dot(g_alpha, p); }
+  void moveto(double alpha) {
+    if (alpha == x_cache_key) return;
+    for (int i = 0; i < N; ++i) x_alpha[i] = x0[i] + alpha * p[i];
+    x_cache_key = alpha;
+  }
+  double wrap_f(double alpha) {
+    if (alpha == f_cache_key) return f_alpha;
+    moveto(alpha);
+    fn->fdf(x_alpha, &f_alpha, nullptr);
+    f_cache_key = alpha;
+    return f_alpha;
+  }
+  double wrap_df(double alpha) {
+    if (alpha == df_cache_key) return df_alpha;
+    moveto(alpha);
+    if (alpha != g_cache_key) {
+      double dummy;
+      fn->fdf(x_alpha, &dummy, g_alpha);
+      g_cache_key = alpha;
+    }
+    df_alpha = slope();
+    df_cache_key = alpha;
+    return df_alpha;
+  }
+  void wrap_fdf(double alpha, double* fo, double* dfo) {
+    if (alpha == f_cache_key && alpha == df_cache_key) {
+      *fo = f_alpha;
+      *dfo = df_alpha;
+      return;
+    }
+    if (alpha == f_cache_key || alpha == df_cache_key) {
+      *fo = wrap_f(alpha);
+      *dfo = wrap_df(alpha);
+      return;
+    }
+    moveto(alpha);
+    fn->fdf(x_alpha, &f_alpha, g_alpha);
+    f_cache_key = alpha;
+    g_cache_key = alpha;
+    df_alpha = slope();
+    df_cache_key = alpha;
+    *fo = f_alpha;
+    *dfo = df_alpha;
+  }
+  void change_direction() {
+    std::memcpy(x_alpha, x0, sizeof(x_alpha));
+    x_cache_key = 0.0;
+    f_cache_key = 0.0;
+    std::memcpy(g_alpha, g0, sizeof(g_alpha));
+    g_cache_key = 0.0;
+    df_alpha = slope();
+    df_cache_key = 0.0;
+  }
+  void init(const double* x) {
+    delta_f = 0;
+    std::memset(dx, 0, sizeof(dx));
+    fn->fdf(x, &f, gradient);
+    std::memcpy(x0, x, sizeof(x0));
+    std::memcpy(g0, gradient, sizeof(g0));
+    g0norm = norm(g0);
+    for (int i = 0; i < N; ++i) p[i] = gradient[i] * (-1.0 / g0norm);
+    pnorm = norm(p);
+    fp0 = -g0norm;
+    std::memcpy(x_alpha, x0, sizeof(x_alpha));
+    x_cache_key = 0;
+    f_alpha = f;
+    f_cache_key = 0;
+    std::memcpy(g_alpha, g0, sizeof(g_alpha));
+    g_cache_key = 0;
+    df_alpha = slope();
+    df_cache_key = 0;
+  }
+  static int solve_quadratic(double a, double b, double c, double* r0, double* r1) {
+    if (a == 0) {
+      if (b == 0) return 0;
+      *r0 = -c / b;
+      return 1;
+    }
+    double disc = b * b - 4 * a * c;
+    if (disc > 0) {
+      if (b == 0) {
+        double r = std::sqrt(-c / a);
+        *r0 = -r;
+        *r1 = r;
+      } else {
+        double sgnb = (b > 0 ? 1 : -1);
+        double temp = -0.5 * (b + sgnb * std::sqrt(disc));
+        double ra = temp / a, rb = c / temp;
+        if (ra < rb) {
+          *r0 = ra;
+          *r1 = rb;
+        } else {
+          *r0 = rb;
+          *r1 = ra;
+        }
+      }
+      return 2;
+    } else if (disc == 0) {
+      *r0 = -0.5 * b / a;
+      *r1 = -0.5 * b / a;
+      return 2;
+    }
+    return 0;
+  }
+  static double cubic(double c0, double c1, double c2, double c3, double z) { return c0 + z * (c1 + z * (c2 + z * c3)); }
+  static void check_extremum(double c0, double c1, double c2, double c3, double z, double* zmin, double* fmin) {
+    double y = cubic(c0, c1, c2, c3, z);
+    if (y < *fmin) {
+      *zmin = z;
+      *fmin = y;
+    }
+  }
+  static double interp_cubic(double f0, double fp0_, double f1, double fp1, double zl, double zh) {
+    double eta = 3 * (f1 - f0) - 2 * fp0_ - fp1;
+    double xi = fp0_ + fp1 - 2 * (f1 - f0);
+    double c0 = f0, c1 = fp0_, c2 = eta, c3 = xi;
+    double zmin = zl, fmin = cubic(c0, c1, c2, c3, zl);
+    check_extremum(c0, c1, c2, c3, zh, &zmin, &fmin);
+    double z0 = 0, z1 = 0;
+    int n = solve_quadratic(3 * c3, 2 * c2, c1, &z0, &z1);
+    if (n == 2) {
+      if (z0 > zl && z0 < zh) check_extremum(c0, c1, c2, c3, z0, &zmin, &fmin);
+      if (z1 > zl && z1 < zh) check_extremum(c0, c1, c2, c3, z1, &zmin, &fmin);
+    } else if (n == 1) {
+      if (z0 > zl && z0 < zh) check_extremum(c0, c1, c2, c3, z0, &zmin, &fmin);
+    }
+    return zmin;
+  }
+  static double interp_quad(double f0, double fp0_, double f1, double zl, double zh) {
+    double fl = f0 + zl * (fp0_ + zl * (f1 - f0 - fp0_));
+    double fh = f0 + zh * (fp0_ + zh * (f1 - f0 - fp0_));
+    double c = 2 * (f1 - f0 - fp0_);
+    double zmin = zl, fmin = fl;
+    if (fh < fmin) {
+      zmin = zh;
+      fmin = fh;
+    }
+    if (c > 0) {
+      double z = -fp0_ / c;
+      if (z > zl && z < zh) {
+        double fz = f0 + z * (fp0_ + z * (f1 - f0 - fp0_));
+        if (fz < fmin) {
+          zmin = z;
+          fmin = fz;
+        }
+      }
+    }
+    return zmin;
+  }
+  double interpolate(double a, double fa, double fpa, double b, double fb, double fpb, double xmin, double xmax) const {
+    double zmin = (xmin - a) / (b - a), zmax = (xmax - a) / (b - a);
+    if (zmin > zmax) std::swap(zmin, zmax);
+    double z;
+    if (order > 2 && std::isfinite(fpb))
+      z = interp_cubic(fa, fpa * (b - a), fb, fpb * (b - a), zmin, zmax);
+    else
+      z = interp_quad(fa, fpa * (b - a), fb, zmin, zmax);
+    return a + z * (b - a);
+  }
+  int line_search(double alpha1, double* alpha_new) {
+    double f0_, fp0_, falpha, falpha_prev, fpalpha = 0, fpalpha_prev, delta, alpha_next;
+    double alpha = alpha1, alpha_prev = 0.0;
+    double a, b, fa, fb, fpa, fpb;
+    const int bracket_iters = 100, section_iters = 100;
+    int i = 0;
+    wrap_fdf(0.0, &f0_, &fp0_);
+    falpha_prev = f0_;
+    fpalpha_prev = fp0_;
+    a = 0.0;
+    b = alpha;
+    fa = f0_;
+    fb = 0.0;
+    fpa = fp0_;
+    fpb = 0.0;
+    while (i++ < bracket_iters) {
+      falpha = wrap_f(alpha);
+      if (falpha > f0_ + alpha * rho * fp0_ || falpha >= falpha_prev) {
+        a = alpha_prev;
+        fa = falpha_prev;
+        fpa = fpalpha_prev;
+        b = alpha;
+        fb = falpha;
+        fpb = std::numeric_limits<double>::quiet_NaN();
+        break;
+      }
+      fpalpha = wrap_df(alpha);
+      if (std::fabs(fpalpha) <= -sigma * fp0_) {
+        *alpha_new = alpha;
+        return kSuccess;
+      }
+      if (fpalpha >= 0) {
+        a = alpha;
+        fa = falpha;
+        fpa = fpalpha;
+        b = alpha_prev;
+        fb = falpha_prev;
+        fpb = fpalpha_prev;
+        break;
+      }
+      delta = alpha - alpha_prev;
+      {
+        double lower = alpha + delta, upper = alpha + tau1 * delta;
+        alpha_next = interpolate(alpha_prev, falpha_prev, fpalpha_prev, alpha, falpha, fpalpha, lower, upper);
+      }
+      alpha_prev = alpha;
+      falpha_prev = falpha;
+      fpalpha_prev = fpalpha;
+      alpha = alpha_next;
+    }
+    while (i++ < section_iters) {
+      delta = b - a;
+      {
+        double lower = a + tau2 * delta, upper = b - tau3 * delta;
+        alpha = interpolate(a, fa, fpa, b, fb, fpb, lower, upper);
+      }
+      falpha = wrap_f(alpha);
+      if ((a - alpha) * fpa <= kDblEps) return kNoProgress;
+      if (falpha > f0_ + rho * alpha * fp0_ || falpha >= fa) {
+        b = alpha;
+        fb = falpha;
+        fpb = std::numeric_limits<double>::quiet_NaN();
+      } else {
+        fpalpha = wrap_df(alpha);
+        if (std::fabs(fpalpha) <= -sigma * fp0_) {
+          *alpha_new = alpha;
+          return kSuccess;
+        }
+        if (((b - a) >= 0 && fpalpha >= 0) || ((b - a) <= 0 && fpalpha <= 0)) {
+          b = a;
+          fb = fa;
+          fpb = fpa;
+          a = alpha;
+          fa = falpha;
+          fpa = fpalpha;
+        } else {
+          a = alpha;
+          fa = falpha;
+          fpa = fpalpha;
+        }
+      }
+    }
+    return kSuccess;
+  }
+  int one_step(double* x) {
+    double alpha = 0.0, alpha1;
+    double f0_ = f;
+    if (pnorm == 0.0 || g0norm == 0.0 || fp0 == 0) {
+      std::memset(dx, 0, sizeof(dx));
+      return kNoProgress;
+    }
+    if (delta_f < 0) {
+      double del = std::max(-delta_f, 10 * kDblEps * std::fabs(f0_));
+      alpha1 = std::min(1.0, 2.0 * del / (-fp0));
+    } else {
+      alpha1 = std::fabs(kStepSize);
+    }
+    int status = line_search(alpha1, &alpha);
+    if (status != kSuccess) return status;
+    {
+      double fa_, dfa_;
+      wrap_fdf(alpha, &fa_, &dfa_);
+      f = f_alpha;
+      std::memcpy(x, x_alpha, sizeof(x_alpha));
+      std::memcpy(gradient, g_alpha, sizeof(g_alpha));
+    }
+    delta_f = f - f0_;
+    {
+      double dx0[N], dg0[N];
+      for (int i = 0; i < N; ++i) {
+        dx0[i] = x[i] - x0[i];
+        dx[i] = dx0[i];
+        dg0[i] = gradient[i] - g0[i];
+      }
+      double dxg = dot(dx0, gradient), dgg = dot(dg0, gradient), dxdg = dot(dx0, dg0), dgnorm = norm(dg0), A, B;
+      if (dxdg != 0) {
+        B = dxg / dxdg;
+        A = -(1.0 + dgnorm * dgnorm / dxdg) * B + dgg / dxdg;
+      } else {
+        B = 0;
+        A = 0;
+      }
+      for (int i = 0; i < N; ++i) p[i] = gradient[i] - A * dx0[i] - B * dg0[i];
+    }
+    std::memcpy(g0, gradient, sizeof(g0));
+    std::memcpy(x0, x, sizeof(x0));
+    g0norm = norm(g0);
+    pnorm = norm(p);
+    double dir = (dot(p, gradient) > 0) ? -1.0 : 1.0;
+    for (int i = 0; i < N; ++i) p[i] *= dir / pnorm;
+    pnorm = norm(p);
+    fp0 = dot(p, g0);
+    change_direction();
+    return kSuccess;
+  }
+  int test_gradient(double epsabs) const { return norm(gradient) < epsabs ? kSuccess : kRunning; }
+};
+
+// K5 driver: covariances of `n` points whose grid is `g` -> cov (9 doubles per point, original order)
+int compute_covariances(b2icp_handle* h, GridSlot& g, size_t n, DeviceBuf& cov) {
+  const int k = h->params.k_correspondences;
+  if (k < 1 || k > kMaxK) return fail(h, B2ICP_ERR_INVALID_ARG, "k_correspondences must be in [1, 32]");
+  if ((size_t)k > n) return fail(h, B2ICP_ERR_TOO_FEW_POINTS, "fewer points than k_correspondences");
+  CK(cov.ensure(n * 9 * sizeof(double)));
+  CK(h->unres_list.ensure(n * sizeof(int)));
+  zero_counter<<<1, 1, 0, h->stream>>>(h->unres_count.as<unsigned int>());
+  knn_cov_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(g.view, g.pts, (int)n, k, h->params.gicp_epsilon, 6,
+                                                                     cov.as<double>(), h->unres_list.as<int>(),
+                                                                     h->unres_count.as<unsigned int>());
+  knn_cov_fallback<<<148 * 4, 128, 0, h->stream>>>(g.view, g.pts, k, h->params.gicp_epsilon, h->unres_list.as<int>(),
+                                                   h->unres_count.as<unsigned int>(), cov.as<double>());
+  h->launches += 3;
+  return B2ICP_OK;
+}
+
+// GICP::computeTransformation for slot 0 (Registration::align around it); fills h->h_states[0].
+int run_gicp(b2icp_handle* h, const float* guess16) {
+  ScanSlot& s = slot(h, 0);
+  GridSlot& g = gslot(h, s.grid);
+  const size_t n = s.src.n;
+  int rc = ensure_slot_work(h, s);
+  if (rc) return rc;
+  // covariances: target (cached with its grid) and source (own temporary grid)
+  if (!g.cov_valid) {
+    rc = compute_covariances(h, g, (size_t)g.view.n, g.cov);
+    if (rc) return rc;
+    g.cov_valid = true;
+  }
+  {
+    GridSlot& sg = gslot(h, kMaxBatch + 1);
+    sg.pts = s.src.raw.as<float4>();
+    GridSlot* gp = &sg;
+    size_t nn = n;
+    rc = build_grids(h, &gp, &nn, 1);
+    if (rc) return rc;
+    rc = compute_covariances(h, sg, n, s.cov);
+    if (rc) return rc;
+  }
+  const int nblk = (int)((n + kGicpThreads - 1) / kGicpThreads);
+  CK(s.mahal.ensure(n * 9 * sizeof(double)));
+  CK(s.gicp_partials.ensure((size_t)nblk * kGicpSums * sizeof(double)));
+  if (h->h_gicp_partials_cap < (size_t)nblk * kGicpSums) {
+    if (h->h_gicp_partials) cudaFreeHost(h->h_gicp_partials);
+    h->h_gicp_partials = nullptr;
+    h->h_gicp_partials_cap = 0;
+    CK(cudaMallocHost((void**)&h->h_gicp_partials, (size_t)nblk * kGicpSums * sizeof(double) * 2));
+    h->h_gicp_partials_cap = (size_t)nblk * kGicpSums * 2;
+  }
+
+  float guess[16], T[16], prevT[16];
+  for (int i = 0; i < 16; ++i) {
+    guess[i] = guess16 ? guess16[i] : ((i % 5 == 0) ? 1.f : 0.f);
+    T[i] = (i % 5 == 0) ? 1.f : 0.f;
+  }
+  std::memcpy(prevT, T, sizeof(T));
+  const b2icp_params& p = h->params;
+  const double dist_threshold = p.max_correspondence_distance * p.max_correspondence_distance;
+  int iters = 0, converged = 0, status = B2ICP_OK;
+  long n_corr = 0;
+  GicpHostFunctor fn;
+  fn.h = h;
+  fn.s = &s;
+  fn.g = &g;
+  std::memcpy(fn.base, guess, sizeof(guess));
+  const int max_rings = rings_for_bound(h, (double)g.view.cell);
+
+  while (!converged) {
+    GicpIterArgs a;
+    std::memcpy(a.guess, guess, sizeof(guess));
+    std::memcpy(a.T, T, sizeof(T));
+    double TR[16];
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) {
+        double sum = 0;
+        for (int kk = 0; kk < 4; ++kk) sum += (double)T[4 * i + kk] * (double)guess[4 * kk + j];
+        TR[4 * i + j] = sum;
+      }
+    const double R[9] = {TR[0], TR[1], TR[2], TR[4], TR[5], TR[6], TR[8], TR[9], TR[10]};
+    std::memcpy(a.R, R, sizeof(R));
+    a.max2 = dist_threshold;
+    a.bound2 = h->cfg.bound2;
+    a.max_rings = max_rings;
+    a.use_seed = iters > 0;
+    gicp_corr_kernel<<<(unsigned)((n + kSweepThreads - 1) / kSweepThreads), kSweepThreads, 0, h->stream>>>(
+        g.view, s.src.raw.as<float4>(), (int)n, a, s.cov.as<double>(), g.cov.as<double>(), s.mahal.as<double>(),
+        s.corr_idx.as<int>(), s.corr_d2.as<float>(), s.corr_pos.as<int>());
+    h->launches += 1;
+    std::memcpy(prevT, T, sizeof(T));
+    // estimateRigidTransformationBFGS
+    double x[6] = {(double)T[3], (double)T[7], (double)T[11], std::atan2((double)T[9], (double)T[10]),
+                   std::asin(-(double)T[8]), std::atan2((double)T[4], (double)T[0])};
+    GicpBFGS bfgs;
+    bfgs.fn = &fn;
+    bfgs.init(x);  // the first evaluation also counts the correspondences
+    if (fn.rc) return fn.rc;
+    n_corr = fn.m;
+    if (n_corr < 4) {  // NotEnoughPointsException -> break, converged_ stays false
+      status = B2ICP_ERR_NOT_ENOUGH_CORRESPONDENCES;
+      break;
+    }
+    int inner = 0, result;
+    do {
+      ++inner;
+      result = bfgs.one_step(x);
+      if (result) break;
+      result = bfgs.test_gradient(1e-2);
+    } while (result == GicpBFGS::kRunning && inner < p.max_inner_iterations);
+    if (fn.rc) return fn.rc;
+    if (!(result == GicpBFGS::kNoProgress || result == GicpBFGS::kSuccess || inner == p.max_inner_iterations)) {
+      status = B2ICP_ERR_SOLVER_FAILED;
+      break;
+    }
+    for (int e = 0; e < 16; ++e) T[e] = (e % 5 == 0) ? 1.f : 0.f;
+    GicpHostFunctor::apply_state(T, x);
+    double delta = 0.;
+    for (int kk = 0; kk < 4; ++kk)
+      for (int l = 0; l < 4; ++l) {
+        double ratio = (kk < 3 && l < 3) ? 1. / p.rotation_epsilon : 1. / p.transformation_epsilon;
+        double c_delta = ratio * std::fabs((double)(prevT[4 * kk + l] - T[4 * kk + l]));
+        if (c_delta > delta) delta = c_delta;
+      }
+    ++iters;
+    if (iters >= p.max_iterations || delta < 1) {
+      converged = 1;
+      std::memcpy(prevT, T, sizeof(T));
+    }
+  }
+  // final_transformation_ = previous_transformation_ * guess (Matrix4f product)
+  IcpState& st = h->h_states[0];
+  std::memset(&st, 0, sizeof(st));
+  for (int r = 0; r < 4; ++r)
+    for (int c = 0; c < 4; ++c) {
+      float sum = 0.f;
+      for (int kk = 0; kk < 4; ++kk) sum += prevT[4 * r + kk] * guess[4 * kk + c];
+      st.final_T[4 * r + c] = sum;
+    }
+  st.converged = converged;
+  st.iter = iters;
+  st.n_corr = (int)n_corr;
+  st.status = status;
+  st.mse = std::nan("");
+  h->timing.kernel_launches = h->launches;
+  h->gicp_evals = fn.evals;
+  // the device copy of the state feeds b2icp_fitness / the aligned-cloud transform
+  ScanTask& t = h->h_tasks[0];
+  t.grid = g.view;
+  t.src = s.src.raw.as<float4>();
+  t.cur = s.cur.as<float4>();
+  t.corr_idx = s.corr_idx.as<int>();
+  t.corr_d2 = s.corr_d2.as<float>();
+  t.corr_pos = s.corr_pos.as<int>();
+  t.partials = s.partials.as<double>();
+  t.state = h->states.as<IcpState>();
+  t.n = (int)n;
+  t.pad = 0;
+  CK(cudaMemcpyAsync(h->tasks.p, h->h_tasks, sizeof(ScanTask), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->states.p, h->h_states, sizeof(IcpState), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return B2ICP_OK;
+}

@@ -91,7 +91,7 @@ EXPORTS = [
     "b2icp_set_source", "b2icp_set_target_device", "b2icp_set_source_device", "b2icp_promote_source_to_target",
     "b2icp_align", "b2icp_fitness", "b2icp_get_correspondences", "b2icp_nn_search", "b2icp_nn_search_device",
     "b2icp_transform_cloud", "b2icp_transform_cloud_f", "b2icp_align_batch", "b2icp_align_batch_device",
-    "b2icp_set_stream", "b2icp_get_timing",
+    "b2icp_set_stream", "b2icp_compute_covariances", "b2icp_get_timing",
     "b2icp_get_grid_info", "b2icp_host_alloc", "b2icp_host_free", "b2icp_last_error", "b2icp_status_string",
     "b2icp_version",
 ]
@@ -131,6 +131,7 @@ def load_library() -> C.CDLL:
                                     C.c_size_t, C.c_int, C.POINTER(Result)]
     L.b2icp_align_batch_device.argtypes = L.b2icp_align_batch.argtypes
     L.b2icp_set_stream.argtypes = [vp, vp]
+    L.b2icp_compute_covariances.argtypes = [vp, vp, C.c_size_t, dp]
     L.b2icp_get_timing.argtypes = [vp, C.POINTER(Timing)]
     L.b2icp_get_grid_info.argtypes = [vp, fp, ip, dp]
     L.b2icp_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
@@ -351,6 +352,14 @@ class Registration:
         res = (Result * n)()
         rc = self._L.b2icp_align_batch_device(self._h, sp, sn, None, None, n, 1 if with_fitness else 0, res)
         return rc, list(res)
+
+    def computeCovariances(self, cloud) -> np.ndarray:
+        """GICP::computeCovariances of a cloud: float64[N,3,3]."""
+        c = _cloud(cloud)
+        out = np.empty((len(c), 3, 3), np.float64)
+        self._check(self._L.b2icp_compute_covariances(self._h, _ptr(c), len(c), out.ctypes.data_as(C.POINTER(C.c_double))),
+                    "compute_covariances")
+        return out
 
     def setStream(self, cuda_stream: int):
         self._check(self._L.b2icp_set_stream(self._h, C.c_void_p(cuda_stream)), "set_stream")

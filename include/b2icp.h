@@ -181,6 +181,12 @@ int b2icp_align_batch_device(b2icp_handle* h, const float* const* d_src, const s
  * so that device-resident pipelines can order their own kernels and events around the ABI calls. */
 int b2icp_set_stream(b2icp_handle* h, void* cuda_stream);
 
+/* GeneralizedIterativeClosestPoint::computeCovariances (reached from icp.align() at icp_odometer.cpp:198,
+ * octree_mapper.cpp:114): for each of the n points the covariance of its k_correspondences nearest
+ * neighbours (itself included), eigenvalues replaced by (1, 1, gicp_epsilon).  cov9 = n x 9 doubles,
+ * row-major 3x3, in input order.  Returns B2ICP_ERR_TOO_FEW_POINTS when n < k_correspondences. */
+int b2icp_compute_covariances(b2icp_handle* h, const float* xyzw, size_t n, double* cov9);
+
 int b2icp_get_timing(b2icp_handle* h, b2icp_timing* out);
 /* Neighbour grid of the current target (the structure that replaces the FLANN k-d tree): cell edge,
  * dims3 = {nx, ny, nz}, mean points per occupied cell.  Any pointer may be NULL. */

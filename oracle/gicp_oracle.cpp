@@ -138,29 +138,55 @@ void compute_r_derivative(const double* x, const double* R, double* g) {
   g[5] = inner(dpsi);
 }
 
+/* The fixed reduction tree of the device kernels (icpslam_b200/csrc/gicp.cuh), restated so that both
+ * sides see bit-identical sums: values are taken in source-index order (0.0 for points without a
+ * correspondence) in blocks of 256; inside a block every 32-value group is reduced by the xor butterfly
+ * 16, 8, 4, 2, 1, the eight group sums are added in order, and the block sums are added in order.
+ * PCL adds serially; that differs in the last bits only, which PCL's own result does not survive either
+ * (tests/test_oracle.py::test_gicp_is_roundoff_sensitive). */
+double tree_sum(const double* v, size_t n) {
+  double total = 0.0;
+  for (size_t b = 0; b < n; b += 256) {
+    double bs = 0.0;
+    const size_t bend = std::min(n, b + 256);
+    for (size_t w = b; w < bend; w += 32) {
+      double t[32], u[32];
+      for (int l = 0; l < 32; ++l) t[l] = (w + l < n) ? v[w + l] : 0.0;
+      for (int o = 16; o > 0; o >>= 1) {
+        for (int l = 0; l < 32; ++l) u[l] = t[l] + t[l ^ o];
+        std::memcpy(t, u, sizeof(t));
+      }
+      bs += t[0];
+    }
+    total += bs;
+  }
+  return total;
+}
+
 /* ---- the cost functor (OptimizationFunctorWithIndices) ------------------------------------------ */
 struct Functor {
   const float* src;                  /* `output` = untransformed source, xyzw */
   const float* tgt;
-  const std::vector<int>* idx_src;
-  const std::vector<int>* idx_tgt;
+  size_t ns = 0;
+  const int32_t* corr = nullptr;     /* per source point: target index or -1 */
+  long m = 0;                        /* number of correspondences */
   const std::vector<double>* mahalanobis; /* 9 per source point */
   float base[16];                    /* base_transformation_ */
   int threads;
   bool exact_double = false;
   long evals = 0;
+  std::vector<double> terms;         /* 13 x ns: f, g0..g2, R00..R22 */
 
   void fdf(const double* x, double* f, double* g) {
     ++evals;
     float Tx[16];
     std::memcpy(Tx, base, sizeof(Tx));
     apply_state(Tx, x);
-    const long m = (long)idx_src->size();
-    double fs = 0, g0 = 0, g1 = 0, g2 = 0;
-    double R[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (long i = 0; i < m; ++i) {
-      const float* ps = src + 4 * (size_t)(*idx_src)[i];
-      const float* pt = tgt + 4 * (size_t)(*idx_tgt)[i];
+    terms.assign(13 * ns, 0.0);
+    for (size_t i = 0; i < ns; ++i) {
+      if (corr[i] < 0) continue;
+      const float* ps = src + 4 * i;
+      const float* pt = tgt + 4 * (size_t)corr[i];
       double res[3];
       if (!exact_double) {
         float pp[3];
@@ -179,26 +205,27 @@ struct Functor {
         for (int r = 0; r < 3; ++r)
           res[r] = Rd[3 * r] * ps[0] + Rd[3 * r + 1] * ps[1] + Rd[3 * r + 2] * ps[2] + x[r] - (double)pt[r];
       }
-      const double* M = &(*mahalanobis)[9 * (size_t)(*idx_src)[i]];
+      const double* M = &(*mahalanobis)[9 * i];
       double tmp[3] = {M[0] * res[0] + M[1] * res[1] + M[2] * res[2], M[3] * res[0] + M[4] * res[1] + M[5] * res[2],
                        M[6] * res[0] + M[7] * res[1] + M[8] * res[2]};
-      fs += res[0] * tmp[0] + res[1] * tmp[1] + res[2] * tmp[2];
-      if (g) {
-        g0 += tmp[0];
-        g1 += tmp[1];
-        g2 += tmp[2];
-        float pb[3];
-        xform_f(base, ps, pb);
-        for (int r = 0; r < 3; ++r)
-          for (int c = 0; c < 3; ++c) R[3 * r + c] += (double)pb[r] * tmp[c];
-      }
+      terms[0 * ns + i] = res[0] * tmp[0] + res[1] * tmp[1] + res[2] * tmp[2];
+      terms[1 * ns + i] = tmp[0];
+      terms[2 * ns + i] = tmp[1];
+      terms[3 * ns + i] = tmp[2];
+      float pb[3];
+      xform_f(base, ps, pb);
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) terms[(4 + 3 * r + c) * ns + i] = (double)pb[r] * tmp[c];
     }
-    if (f) *f = fs / (double)m;
+    double S[13];
+    for (int k = 0; k < 13; ++k) S[k] = tree_sum(&terms[(size_t)k * ns], ns);
+    if (f) *f = S[0] / (double)m;
     if (g) {
-      g[0] = g0 * 2.0 / (double)m;
-      g[1] = g1 * 2.0 / (double)m;
-      g[2] = g2 * 2.0 / (double)m;
-      for (int k = 0; k < 9; ++k) R[k] *= 2.0 / (double)m;
+      g[0] = S[1] * 2.0 / (double)m;
+      g[1] = S[2] * 2.0 / (double)m;
+      g[2] = S[3] * 2.0 / (double)m;
+      double R[9];
+      for (int k = 0; k < 9; ++k) R[k] = S[4 + k] * (2.0 / (double)m);
       compute_r_derivative(x, R, g);
     }
   }
@@ -618,9 +645,7 @@ int b2o_align_gicp_impl(const b2icp_params* p, const float* src, size_t ns, cons
     for (int e = 0; e < 9; ++e) mahal[9 * i + e] = (e % 4 == 0) ? 1.0 : 0.0;
   std::vector<float> query(4 * ns), d2(ns);
   std::vector<int32_t> nn(ns);
-  std::vector<int> idx_src, idx_tgt;
-  idx_src.reserve(ns);
-  idx_tgt.reserve(ns);
+  std::vector<int32_t> corr_now(ns);
   const double dist_threshold = p->max_correspondence_distance * p->max_correspondence_distance;
   int iters = 0, converged = 0, status = B2ICP_OK, n_corr = 0;
   double mse = std::numeric_limits<double>::quiet_NaN();
@@ -649,9 +674,8 @@ int b2o_align_gicp_impl(const b2icp_params* p, const float* src, size_t ns, cons
     st->nn += ms_since(tn);
 
     auto ts = clk::now();
-    idx_src.clear();
-    idx_tgt.clear();
     double dsum = 0;
+    n_corr = 0;
     for (size_t i = 0; i < ns; ++i) {
       const bool keep = nn[i] >= 0 && (double)d2[i] < dist_threshold; /* strict < */
       if (keep) {
@@ -662,14 +686,13 @@ int b2o_align_gicp_impl(const b2icp_params* p, const float* src, size_t ns, cons
         mat3_mul_bt(M, R, temp);
         for (int e = 0; e < 9; ++e) temp[e] += C2[e];
         mat3_inv(temp, &mahal[9 * i]);
-        idx_src.push_back((int)i);
-        idx_tgt.push_back(nn[i]);
+        ++n_corr;
         dsum += (double)d2[i];
       }
+      corr_now[i] = keep ? nn[i] : -1;
       if ((record_iter == iters || record_iter < 0) && corr_idx) corr_idx[i] = keep ? nn[i] : -1;
       if ((record_iter == iters || record_iter < 0) && corr_d2) corr_d2[i] = d2[i];
     }
-    n_corr = (int)idx_src.size();
     mse = n_corr ? dsum / n_corr : std::numeric_limits<double>::quiet_NaN();
     std::memcpy(prevT, T, sizeof(T));
     if (n_corr < 4) { /* NotEnoughPointsException -> break, converged_ stays false */
@@ -683,8 +706,9 @@ int b2o_align_gicp_impl(const b2icp_params* p, const float* src, size_t ns, cons
     Functor fn;
     fn.src = src;
     fn.tgt = tgt;
-    fn.idx_src = &idx_src;
-    fn.idx_tgt = &idx_tgt;
+    fn.ns = ns;
+    fn.corr = corr_now.data();
+    fn.m = n_corr;
     fn.mahalanobis = &mahal;
     std::memcpy(fn.base, guess, sizeof(guess));
     fn.threads = threads;
