@@ -231,6 +231,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="sweeps per GPU per step")
     ap.add_argument("--impl", default="b2icp", choices=["b2icp", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=4, help="sweeps timed on the CPU oracle (rank 0, N=1)")
+    ap.add_argument("--grid-cell", type=float, default=0.0, help="neighbour-grid cell edge in metres (0 = auto); tuning only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b2icp" else args.warmup
 
@@ -267,7 +268,7 @@ def main():
         map_xyzw, sweeps = load_workload(rank * args.batch, args.batch)
 
     stream = torch.cuda.current_stream()
-    reg = R.Registration(preset=R.PRESET_MAPPER, device=local_rank, profile=1)
+    reg = R.Registration(preset=R.PRESET_MAPPER, device=local_rank, profile=1, grid_cell=args.grid_cell)
     reg.setStream(stream.cuda_stream)
     reg.setInputTarget(map_xyzw)
     grid = reg.gridInfo()

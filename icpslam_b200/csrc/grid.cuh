@@ -234,3 +234,75 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply(int* __restrict__ dat
 }
 
 }  // namespace b2
+
+// ---- K8: pcl::VoxelGrid<PointXYZ>::applyFilter (reference src/icpslam/icp_odometer.cpp:96-101; SURVEY.md
+// App. A.8) as a counting sort over the dense voxel table plus one centroid pass ---------------------------
+namespace b2 {
+
+struct VoxelParams {
+  float inv_leaf;         // 1 / leaf (float division, like Eigen::Array4f::Ones() / leaf_size_)
+  int min_b[3];           // floor(min_p * inv_leaf)
+  int div[3];             // max_b - min_b + 1
+};
+
+// PCL: ijk = static_cast<int>(floor(p * inverse_leaf_size) - static_cast<float>(min_b));
+//      idx = ijk0 + ijk1 * dx + ijk2 * dx * dy
+__device__ __forceinline__ int voxel_index(float4 v, const VoxelParams& p) {
+  const int i0 = (int)fsub(floorf(fmul(v.x, p.inv_leaf)), (float)p.min_b[0]);
+  const int i1 = (int)fsub(floorf(fmul(v.y, p.inv_leaf)), (float)p.min_b[1]);
+  const int i2 = (int)fsub(floorf(fmul(v.z, p.inv_leaf)), (float)p.min_b[2]);
+  return i0 + i1 * p.div[0] + i2 * p.div[0] * p.div[1];
+}
+
+__global__ void __launch_bounds__(256) voxel_count(const float4* __restrict__ p, int n, VoxelParams vp,
+                                                   int* __restrict__ cell_of, int* __restrict__ rank,
+                                                   int* __restrict__ count) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = voxel_index(__ldg(p + i), vp);
+  cell_of[i] = c;
+  rank[i] = atomicAdd(count + c, 1);
+}
+
+// leader flag per sorted slot: the first slot of every occupied voxel
+__global__ void __launch_bounds__(256) voxel_flag_leaders(int n, const int* __restrict__ cell_of,
+                                                          const int* __restrict__ rank,
+                                                          const int* __restrict__ cell_start, int* __restrict__ flags) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  flags[__ldg(cell_start + __ldg(cell_of + i)) + __ldg(rank + i)] = (__ldg(rank + i) == 0) ? 1 : 0;
+}
+
+// One thread per occupied voxel (its leader slot): float centroid of the voxel's points taken in ORIGINAL
+// index order (what a stable sort by voxel index gives), written at the voxel's rank among occupied
+// voxels = ascending voxel index, PCL's output order.
+__global__ void __launch_bounds__(128) voxel_centroids(const float4* __restrict__ sorted, int n, VoxelParams vp,
+                                                       const int* __restrict__ cell_start,
+                                                       const int* __restrict__ slot_of, float4* __restrict__ out) {
+  int pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= n) return;
+  if (__ldg(slot_of + pos + 1) == __ldg(slot_of + pos)) return;  // not a leader
+  const int c = voxel_index(__ldg(sorted + pos), vp);
+  const int s = __ldg(cell_start + c), e = __ldg(cell_start + c + 1);
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  int last = -1;
+  for (int k = s; k < e; ++k) {  // selection by increasing original index (voxels hold a handful of points)
+    int best = 0x7FFFFFFF, bj = s;
+    for (int j = s; j < e; ++j) {
+      const int id = __float_as_int(__ldg(&sorted[j].w));
+      if (id > last && id < best) {
+        best = id;
+        bj = j;
+      }
+    }
+    const float4 p = __ldg(sorted + bj);
+    sx = fadd(sx, p.x);
+    sy = fadd(sy, p.y);
+    sz = fadd(sz, p.z);
+    last = best;
+  }
+  const float cnt = (float)(e - s);
+  out[__ldg(slot_of + pos)] = make_float4(__fdiv_rn(sx, cnt), __fdiv_rn(sy, cnt), __fdiv_rn(sz, cnt), 1.0f);
+}
+
+}  // namespace b2

@@ -154,15 +154,25 @@ __device__ __forceinline__ NNResult grid_nn(const GridView& g, float qx, float q
         j = s;
         e = s + (int)(m & 0xFFFFu);
       }
+      // two candidates per trip (both loads in flight before either is used); when only one is left
+      // the second slot re-reads it, which cannot change the result
+      const int j1 = (j + 1 < e) ? j + 1 : j;
       const float4 p = __ldg(g.pts + j);
+      const float4 p1 = __ldg(g.pts + j1);
       const float d = sqdist3(qx, qy, qz, p.x, p.y, p.z);
+      const float d1 = sqdist3(qx, qy, qz, p1.x, p1.y, p1.z);
       const unsigned long long k = pack_key(d, __float_as_int(p.w));
+      const unsigned long long k1 = pack_key(d1, __float_as_int(p1.w));
       if (k < r.key) {
         r.key = k;
         r.pos = j;
-        thr = fminf(bound2, d);
       }
-      ++j;
+      if (k1 < r.key) {
+        r.key = k1;
+        r.pos = j1;
+      }
+      thr = fminf(bound2, key_d2(r.key));
+      j += 2;
     }
   }
 

@@ -91,7 +91,7 @@ EXPORTS = [
     "b2icp_set_source", "b2icp_set_target_device", "b2icp_set_source_device", "b2icp_promote_source_to_target",
     "b2icp_align", "b2icp_fitness", "b2icp_get_correspondences", "b2icp_nn_search", "b2icp_nn_search_device",
     "b2icp_transform_cloud", "b2icp_transform_cloud_f", "b2icp_align_batch", "b2icp_align_batch_device",
-    "b2icp_set_stream", "b2icp_compute_covariances", "b2icp_get_timing",
+    "b2icp_set_stream", "b2icp_compute_covariances", "b2icp_voxel_filter", "b2icp_get_timing",
     "b2icp_get_grid_info", "b2icp_host_alloc", "b2icp_host_free", "b2icp_last_error", "b2icp_status_string",
     "b2icp_version",
 ]
@@ -132,6 +132,7 @@ def load_library() -> C.CDLL:
     L.b2icp_align_batch_device.argtypes = L.b2icp_align_batch.argtypes
     L.b2icp_set_stream.argtypes = [vp, vp]
     L.b2icp_compute_covariances.argtypes = [vp, vp, C.c_size_t, dp]
+    L.b2icp_voxel_filter.argtypes = [vp, vp, C.c_size_t, C.c_float, vp, C.POINTER(C.c_size_t)]
     L.b2icp_get_timing.argtypes = [vp, C.POINTER(Timing)]
     L.b2icp_get_grid_info.argtypes = [vp, fp, ip, dp]
     L.b2icp_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
@@ -360,6 +361,14 @@ class Registration:
         self._check(self._L.b2icp_compute_covariances(self._h, _ptr(c), len(c), out.ctypes.data_as(C.POINTER(C.c_double))),
                     "compute_covariances")
         return out
+
+    def voxelFilterCloud(self, cloud, leaf: float) -> np.ndarray:
+        """IcpOdometer::voxelFilterCloud (pcl::VoxelGrid with a cubic leaf)."""
+        c = _cloud(cloud)
+        out = np.empty_like(c)
+        n_out = C.c_size_t()
+        self._check(self._L.b2icp_voxel_filter(self._h, _ptr(c), len(c), leaf, _ptr(out), C.byref(n_out)), "voxel_filter")
+        return out[: n_out.value].copy()
 
     def setStream(self, cuda_stream: int):
         self._check(self._L.b2icp_set_stream(self._h, C.c_void_p(cuda_stream)), "set_stream")

@@ -15,8 +15,8 @@
 //
 // Every registration, transform and search below is a call of the C ABI: there is no CPU path.  The
 // two map operations that the reference delegates to pcl::octree (addPointsToMap's one-point-per-voxel
-// rule, approxNearestNeighbors) are SURVEY.md §8f "next" rows: the map's dedup set lives on the host
-// here, and neighbours come from the engine's EXACT search (documented deviation from PCL's greedy
+// rule, approxNearestNeighbors) are SURVEY.md §8f "next" rows: the map's dedup set (pure bookkeeping, no
+// arithmetic) lives on the host here, and neighbours come from the engine's EXACT search (documented deviation from PCL's greedy
 // approxNearestSearch: never farther than PCL's answer).
 #pragma once
 #include <cmath>
@@ -158,52 +158,13 @@ class Engine {
   b2icp_handle* h_ = nullptr;
 };
 
-// pcl::VoxelGrid<PointXYZ>::applyFilter on the host: centroid per occupied leaf,
-// output in ascending linear voxel index.  (K8 — the GPU version — is a §8f "next" row.)
-inline void voxelGridFilter(const Cloud& in, double leaf, Cloud& out) {
-  out.points.clear();
-  if (in.points.empty() || !(leaf > 0)) return;
-  const float inv = (float)(1.0 / leaf);
-  float mn[3] = {std::numeric_limits<float>::max(), std::numeric_limits<float>::max(), std::numeric_limits<float>::max()};
-  float mx[3] = {-mn[0], -mn[1], -mn[2]};
-  for (const PointXYZ& p : in.points) {
-    if (!std::isfinite(p.x) || !std::isfinite(p.y) || !std::isfinite(p.z)) continue;
-    mn[0] = std::min(mn[0], p.x); mn[1] = std::min(mn[1], p.y); mn[2] = std::min(mn[2], p.z);
-    mx[0] = std::max(mx[0], p.x); mx[1] = std::max(mx[1], p.y); mx[2] = std::max(mx[2], p.z);
-  }
-  long long minb[3], div[3];
-  for (int d = 0; d < 3; ++d) {
-    minb[d] = (long long)std::floor(mn[d] * inv);
-    div[d] = (long long)std::floor(mx[d] * inv) - minb[d] + 1;
-  }
-  if ((double)div[0] * (double)div[1] * (double)div[2] > (double)std::numeric_limits<int32_t>::max()) {
-    out = in;  // PCL warns "leaf size is too small" and returns the input unchanged
-    return;
-  }
-  struct Key { long long idx; uint32_t pt; };
-  std::vector<Key> keys;
-  keys.reserve(in.points.size());
-  for (uint32_t i = 0; i < in.points.size(); ++i) {
-    const PointXYZ& p = in.points[i];
-    if (!std::isfinite(p.x) || !std::isfinite(p.y) || !std::isfinite(p.z)) continue;
-    long long ix = (long long)std::floor(p.x * inv) - minb[0];
-    long long iy = (long long)std::floor(p.y * inv) - minb[1];
-    long long iz = (long long)std::floor(p.z * inv) - minb[2];
-    keys.push_back(Key{ix + iy * div[0] + iz * div[0] * div[1], i});
-  }
-  std::stable_sort(keys.begin(), keys.end(), [](const Key& a, const Key& b) { return a.idx < b.idx; });
-  for (size_t a = 0; a < keys.size();) {
-    size_t b = a;
-    float sx = 0, sy = 0, sz = 0;
-    while (b < keys.size() && keys[b].idx == keys[a].idx) {
-      const PointXYZ& p = in.points[keys[b].pt];
-      sx += p.x; sy += p.y; sz += p.z;
-      ++b;
-    }
-    const float n = (float)(b - a);
-    out.points.push_back(PointXYZ{sx / n, sy / n, sz / n, 1.0f});
-    a = b;
-  }
+// pcl::VoxelGrid<PointXYZ>::filter with a cubic leaf -> b2icp_voxel_filter (K8 on the device).
+inline int voxelGridFilter(b2icp_handle* h, const Cloud& in, double leaf, Cloud& out) {
+  out.points.resize(in.points.size());
+  size_t n_out = 0;
+  int rc = b2icp_voxel_filter(h, in.data(), in.size(), (float)leaf, out.data(), &n_out);
+  out.points.resize(rc == B2ICP_OK ? n_out : 0);
+  return rc;
 }
 
 // ---- IcpOdometer ----------------------------------------------------------------------------------
@@ -246,7 +207,7 @@ class IcpOdometer {
   }
   // icp_odometer.cpp:96-101
   void voxelFilterCloud(Cloud::Ptr* input, Cloud::Ptr* output) {
-    if (prm_.voxel_leaf_size > 0) voxelGridFilter(**input, prm_.voxel_leaf_size, **output);
+    if (prm_.voxel_leaf_size > 0) last_status = voxelGridFilter(engine_.get(), **input, prm_.voxel_leaf_size, **output);
     else **output = **input;
   }
   void publishPath(double) {}

@@ -187,6 +187,13 @@ int b2icp_set_stream(b2icp_handle* h, void* cuda_stream);
  * row-major 3x3, in input order.  Returns B2ICP_ERR_TOO_FEW_POINTS when n < k_correspondences. */
 int b2icp_compute_covariances(b2icp_handle* h, const float* xyzw, size_t n, double* cov9);
 
+/* IcpOdometer::voxelFilterCloud -> pcl::VoxelGrid<PointXYZ>::filter (icp_odometer.cpp:96-101) with leaf size
+ * `leaf` on all three axes: one centroid per occupied leaf, output in ascending voxel index (x fastest),
+ * float accumulation in input order inside a leaf.  out_xyzw must hold n points; *n_out receives the count.
+ * Like PCL, a leaf so small that the voxel count overflows an int returns the input unchanged. */
+int b2icp_voxel_filter(b2icp_handle* h, const float* in_xyzw, size_t n, float leaf, float* out_xyzw,
+                       size_t* n_out);
+
 int b2icp_get_timing(b2icp_handle* h, b2icp_timing* out);
 /* Neighbour grid of the current target (the structure that replaces the FLANN k-d tree): cell edge,
  * dims3 = {nx, ny, nz}, mean points per occupied cell.  Any pointer may be NULL. */

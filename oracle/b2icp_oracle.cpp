@@ -674,6 +674,66 @@ int b2o_fitness(const float* src, size_t ns, const float* tgt, size_t nt, const 
   return B2ICP_OK;
 }
 
+/* pcl::VoxelGrid<PointXYZ>::applyFilter (Appendix A.8) as called by IcpOdometer::voxelFilterCloud
+ * (reference src/icpslam/icp_odometer.cpp:96-101) with a cubic leaf.  PCL's std::sort is unstable, so the
+ * order of the float additions inside a leaf is unspecified there; here it is input order (stable sort).
+ * out must hold n points; returns the number written in *n_out. */
+int b2o_voxel_filter(const float* in, size_t n, float leaf, float* out, size_t* n_out) {
+  if (!n_out) return B2ICP_ERR_INVALID_ARG;
+  *n_out = 0;
+  if (n == 0) return B2ICP_OK;
+  if (!in || !out || !(leaf > 0)) return B2ICP_ERR_INVALID_ARG;
+  if (!all_finite(in, n)) return B2ICP_ERR_NONFINITE_INPUT;
+  const float inv = 1.0f / leaf;
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (size_t i = 0; i < n; ++i)
+    for (int d = 0; d < 3; ++d) {
+      mn[d] = std::min(mn[d], in[4 * i + d]);
+      mx[d] = std::max(mx[d], in[4 * i + d]);
+    }
+  int min_b[3], div[3];
+  long long cells = 1;
+  for (int d = 0; d < 3; ++d) {
+    min_b[d] = (int)std::floor(mn[d] * inv);
+    div[d] = (int)std::floor(mx[d] * inv) - min_b[d] + 1;
+    cells *= div[d];
+    if (cells > (long long)INT32_MAX) { /* "Leaf size is too small": output = input */
+      std::memcpy(out, in, n * 4 * sizeof(float));
+      *n_out = n;
+      return B2ICP_OK;
+    }
+  }
+  std::vector<std::pair<int, uint32_t>> keys(n);
+  for (size_t i = 0; i < n; ++i) {
+    int i0 = (int)(std::floor(in[4 * i] * inv) - (float)min_b[0]);
+    int i1 = (int)(std::floor(in[4 * i + 1] * inv) - (float)min_b[1]);
+    int i2 = (int)(std::floor(in[4 * i + 2] * inv) - (float)min_b[2]);
+    keys[i] = {i0 + i1 * div[0] + i2 * div[0] * div[1], (uint32_t)i};
+  }
+  std::stable_sort(keys.begin(), keys.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+  size_t w = 0;
+  for (size_t a = 0; a < n;) {
+    size_t b = a;
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    while (b < n && keys[b].first == keys[a].first) {
+      const float* p = in + 4 * (size_t)keys[b].second;
+      sx += p[0];
+      sy += p[1];
+      sz += p[2];
+      ++b;
+    }
+    const float cnt = (float)(b - a);
+    out[4 * w] = sx / cnt;
+    out[4 * w + 1] = sy / cnt;
+    out[4 * w + 2] = sz / cnt;
+    out[4 * w + 3] = 1.0f;
+    ++w;
+    a = b;
+  }
+  *n_out = w;
+  return B2ICP_OK;
+}
+
 /* Pose6DOF algebra, reference src/utils/pose6DOF.cpp. pose7 = {px,py,pz,qw,qx,qy,qz}. */
 static void quat_mul(const double* a, const double* b, double* o) { /* w,x,y,z */
   double w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];

@@ -73,6 +73,9 @@ int b2o_align(const b2icp_params* p, const float* src_xyzw, size_t n_src, const 
 int b2o_fitness(const float* src_xyzw, size_t n_src, const float* tgt_xyzw, size_t n_tgt,
                 const float* T16, double max_range, double* out);
 
+/* pcl::VoxelGrid with a cubic leaf (Appendix A.8; reference icp_odometer.cpp:96-101). out holds n points. */
+int b2o_voxel_filter(const float* in_xyzw, size_t n, float leaf, float* out_xyzw, size_t* n_out);
+
 /* Pose6DOF algebra (reference src/utils/pose6DOF.cpp:98-105 compose, :117-122 inverse,
  * :185-190 fromEigenMatrix).  pose7 = {px,py,pz,qw,qx,qy,qz}. */
 void b2o_pose_compose(const double* a7, const double* b7, double* out7);

@@ -255,6 +255,18 @@ def fitness(src, tgt, T, max_range=1.7976931348623157e308):
     return out.value
 
 
+def voxel_filter(cloud, leaf: float) -> np.ndarray:
+    cloud = _cloud(cloud)
+    out = np.empty_like(cloud)
+    n_out = C.c_size_t()
+    L = lib()
+    L.b2o_voxel_filter.argtypes = [C.POINTER(C.c_float), C.c_size_t, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_size_t)]
+    rc = L.b2o_voxel_filter(_f(cloud), len(cloud), leaf, _f(out), C.byref(n_out))
+    if rc != 0:
+        raise RuntimeError(f"b2o_voxel_filter rc={rc}")
+    return out[: n_out.value].copy()
+
+
 def pose_compose(a, b):
     a = np.ascontiguousarray(a, np.float64)
     b = np.ascontiguousarray(b, np.float64)

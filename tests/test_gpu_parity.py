@@ -297,3 +297,30 @@ def test_batch_consecutive_pairs_longer_than_one_chunk(R, oracle):
         o = oracle.align(p, seq[i + 1], seq[i])
         assert res[i].iterations == o["iterations"], i
         assert_transform_close(res[i].matrix(), o["T"])
+
+
+# ------------------------------------------------------------------------------------------------
+# K8: voxel-grid downsample (part of BASELINE configs[4])
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("leaf", [0.2, 0.05, 1.0])
+def test_voxel_filter_bit_exact(R, oracle, leaf):
+    _, _, sw = synth.sweep_sequence(10, 1)
+    reg = R.Registration()
+    out = reg.voxelFilterCloud(sw[0], leaf)
+    ref = oracle.voxel_filter(sw[0], leaf)
+    assert out.shape == ref.shape and len(out) < len(sw[0])
+    assert np.array_equal(out, ref)            # same voxels, same order, same float centroids
+    # idempotent up to re-binning: filtering the centroids again cannot increase the count
+    assert len(reg.voxelFilterCloud(out, leaf)) <= len(out)
+
+
+def test_voxel_filter_edge_cases(R, oracle):
+    reg = R.Registration()
+    one = synth.as_xyzw(np.array([[1.0, -2.0, 3.0], [1.01, -2.01, 3.01]]))
+    assert np.array_equal(reg.voxelFilterCloud(one, 0.5), oracle.voxel_filter(one, 0.5))
+    assert len(reg.voxelFilterCloud(one[:0], 0.5)) == 0
+    wide = synth.as_xyzw(np.array([[0.0, 0, 0], [5000.0, 5000, 5000]]))
+    out = reg.voxelFilterCloud(wide, 0.001)     # voxel count overflows int: PCL returns the input
+    assert np.array_equal(out, wide)
+    _, _, sc = synth.planar_stream(3, 1)
+    assert np.array_equal(reg.voxelFilterCloud(sc[0], 0.1), oracle.voxel_filter(sc[0], 0.1))
