@@ -331,12 +331,13 @@ def main():
         return float(t[0]), float(t[1]), last
 
     # ---- HBM-resident leg -----------------------------------------------------------------------
-    sweep_ms, sweep_launches, iters_hist = [], [], []
+    sweep_ms, sweep_launches, iters_hist, searches = [], [], [], []
 
     def collect(res):
         tm = reg.timing()
         sweep_ms.append(tm.nn_sweep_ms)
         sweep_launches.append(tm.nn_sweep_launches)
+        searches.append(tm.nn_searches)
         iters_hist.append([r.iterations for r in res])
 
     sampler = ClockSampler(local_rank)
@@ -382,7 +383,10 @@ def main():
                 "traffic": traffic, "kernel": "icp_sweep_p2p", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes / max(n_launch, 1),
                 "avg_launch_us": 1e6 * kernel_s / max(n_launch, 1), "launches": n_launch,
-                "nt_touched": nt_touched, "kernel_share_of_step": kernel_s / dev_s}
+                "nt_touched": nt_touched, "kernel_share_of_step": kernel_s / dev_s,
+                # share of (query, iteration) pairs that needed a real search; the rest were settled by the
+                # cached-neighbour certificate (icpslam_b200/csrc/nncache.cuh)
+                "searched_fraction": float(np.sum(searches)) / max(1.0, float(sum(sum(x) for x in iters_hist)) * N_SWEEP)}
 
     # ---- CPU baseline on this box's host cores (bounded sample) -----------------------------------
     cpu = None

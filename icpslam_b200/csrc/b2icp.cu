@@ -42,6 +42,7 @@ constexpr int kUnboundedRings = 3;        // ring budget of unbounded searches b
 // 0.35 m 6337, 0.4 m 6084, 0.5 m 5623): the optimum sits near 2.3 points per occupied cell.
 constexpr double kTargetOccupancy = 2.5;  // points per occupied cell the auto-sizing aims at
 constexpr double kMaxOccupancy = 4.0;     // above this the grid is rebuilt with smaller cells
+constexpr float kCacheMarginFrac = 0.05f;  // nncache.cuh: box-search margin as a fraction of the cell edge
 constexpr int kMaxBatch = 64;             // scans advanced together by one sweep launch
 
 struct DeviceBuf {
@@ -92,11 +93,11 @@ struct GridSlot {
 
 struct ScanSlot {
   Cloud src;
-  DeviceBuf cur, corr_idx, corr_d2, corr_pos, partials;
+  DeviceBuf cur, corr_idx, corr_d2, corr_pos, cand, lb, partials;
   DeviceBuf cov, mahal, gicp_partials;  // GICP: source covariances, Mahalanobis matrices, per-CTA sums
   int grid = 0;
   void release() {
-    for (DeviceBuf* b : {&src.raw, &cur, &corr_idx, &corr_d2, &corr_pos, &partials, &cov, &mahal, &gicp_partials})
+    for (DeviceBuf* b : {&src.raw, &cur, &corr_idx, &corr_d2, &corr_pos, &cand, &lb, &partials, &cov, &mahal, &gicp_partials})
       b->release();
   }
 };
@@ -173,6 +174,8 @@ void derive_config(b2icp_handle* h) {
   c.max_iterations = p.max_iterations;
   c.min_corr = 3;
   c.max_rings = 1;
+  c.margin_frac = kCacheMarginFrac;
+  if (const char* e = getenv("B2ICP_MARGIN")) c.margin_frac = (float)atof(e);  // tuning only
 }
 
 int rings_for_bound(const b2icp_handle* h, double min_cell) {
@@ -342,6 +345,8 @@ int ensure_slot_work(b2icp_handle* h, ScanSlot& s) {
   CK(s.corr_idx.ensure(n * sizeof(int)));
   CK(s.corr_d2.ensure(n * sizeof(float)));
   CK(s.corr_pos.ensure(n * sizeof(int)));
+  CK(s.cand.ensure(n * sizeof(int2)));
+  CK(s.lb.ensure(n * sizeof(float)));
   CK(s.partials.ensure(ncta * kNumSums * sizeof(double)));
   return B2ICP_OK;
 }
@@ -383,6 +388,8 @@ int run_batch(b2icp_handle* h, int B, const float* guesses) {
     t.corr_idx = s.corr_idx.as<int>();
     t.corr_d2 = s.corr_d2.as<float>();
     t.corr_pos = s.corr_pos.as<int>();
+    t.cand = s.cand.as<int2>();
+    t.lb = s.lb.as<float>();
     t.partials = s.partials.as<double>();
     t.state = h->states.as<IcpState>() + i;
     t.n = (int)s.src.n;
@@ -397,7 +404,7 @@ int run_batch(b2icp_handle* h, int B, const float* guesses) {
     st.mse = std::nan("");
     st.prev_mse = DBL_MAX;
   }
-  h->cfg.max_rings = rings_for_bound(h, min_cell);
+  h->cfg.max_rings = rings_for_bound(h, min_cell) + (int)std::ceil(h->cfg.margin_frac) + 1;
   CK(cudaMemcpyAsync(h->tasks.p, h->h_tasks, sizeof(ScanTask) * B, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->states.p, h->h_states, sizeof(IcpState) * B, cudaMemcpyHostToDevice, h->stream));
 
@@ -419,7 +426,9 @@ int run_batch(b2icp_handle* h, int B, const float* guesses) {
   dim3 grid((unsigned)((max_n + (size_t)kSweepThreads * qpt - 1) / ((size_t)kSweepThreads * qpt)), (unsigned)B, 1);
   for (int it = 0; it < iters; ++it) {
     if (prof) CK(cudaEventRecord(h->events[2 + 2 * it], h->stream));
-    if (qpt == 4)
+    if (qpt == 8)
+      icp_sweep_p2p<8><<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>(), h->cfg);
+    else if (qpt == 4)
       icp_sweep_p2p<4><<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>(), h->cfg);
     else if (qpt == 2)
       icp_sweep_p2p<2><<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>(), h->cfg);
@@ -451,6 +460,7 @@ int read_states(b2icp_handle* h, int B) {
       t.nn_sweep_ms += ms;
     }
     t.nn_sweep_launches = ran;
+    for (int i = 0; i < B; ++i) t.nn_searches += h->h_states[i].unresolved;
   }
   h->timing.kernel_launches = h->launches;
   return B2ICP_OK;

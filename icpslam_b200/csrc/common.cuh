@@ -47,7 +47,7 @@ struct IcpState {
   int status;        // b2icp_status of the loop
   int n_corr;        // gated correspondences of the last sweep
   unsigned int ticket;   // last-CTA election counter
-  unsigned int unresolved;  // queries handed to the brute-force fallback (unbounded searches)
+  unsigned int unresolved;  // P2P loop: queries that needed a real search, summed over the iterations
   int pad;
 };
 
@@ -60,7 +60,8 @@ struct IcpConfig {
   float bound2;            // float upper bound of max2 used for pruning
   int max_iterations;
   int min_corr;            // 3 (ICP)
-  int max_rings;           // ring budget before a query is handed to the fallback
+  int max_rings;           // ring budget before a query is handed to the fallback / cell span of a box search
+  float margin_frac;       // nncache.cuh: search-radius margin as a fraction of the grid cell
 };
 
 // One scan: source cloud, running (in-place transformed) cloud, outputs, state.
@@ -71,6 +72,8 @@ struct ScanTask {
   int* corr_idx;       // [n] target index of the last sweep, -1 = gated out
   float* corr_d2;      // [n] float d2 of the last sweep
   int* corr_pos;       // [n] sorted-array position of the last match (seed of the next search), -1 = none
+  int2* cand;          // [n] sorted positions of the nearest / second-nearest target point (nncache.cuh), -1 = none
+  float* lb;           // [n] lower bound on the distance from cur[i] to every target point not in cand[i]
   double* partials;    // [gridDim.x][kNumSums] per-CTA sums
   IcpState* state;
   int n;

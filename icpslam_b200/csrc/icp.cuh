@@ -15,6 +15,7 @@
 #pragma once
 #include "common.cuh"
 #include "nn.cuh"
+#include "nncache.cuh"
 #include "solve.cuh"
 
 namespace b2 {
@@ -66,16 +67,32 @@ __device__ __forceinline__ bool grid_reduce_last(const ScanTask& t, double (*sme
 }
 
 // QPT = queries per thread: consecutive 256-point slabs handled by the same CTA, so that the prologue,
-// the 17-value fp64 reduction and the CTA barrier are paid once per QPT queries (batches use 4; a
-// single scan uses 1 to keep every SM busy).
+// the 17-value fp64 reduction and the CTA barriers are paid once per QPT queries, and so that the
+// compacted list of queries that need a real search is long enough to fill the CTA's warps.
+//
+// Three phases per CTA (nncache.cuh explains the certificate):
+//   A  every query: q = T_inc * q (in place), distances to its two cached candidates, certificate
+//      test; passers get their correspondence at once, the others are compacted (ballot + prefix, so
+//      the list order is deterministic) into a shared-memory work list;
+//   B  the work list, one entry per thread: exact box search, new candidates + bound;
+//   C  every query again, in (thread, slab) order: the 17 fp64 sums from the stored correspondences —
+//      the summation order does not depend on which queries were searched, so results are
+//      bit-reproducible, and the 34 accumulator registers are not live during the search.
 template <int QPT>
 __global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) icp_sweep_p2p(const ScanTask* __restrict__ tasks, IcpConfig cfg) {
-  __shared__ double smem[kSweepThreads / 32][kNumSums];
+  constexpr int kWarps = kSweepThreads / 32;
+  constexpr int kSlab = QPT * kSweepThreads;  // queries per CTA
+  __shared__ double smem[kWarps][kNumSums];
   __shared__ NNScratch<kSweepThreads> sc;
   __shared__ float sT[16];
   __shared__ int s_flags[2];
+  __shared__ float wl_thr[kSlab];            // per local query: squared distance of its best cached candidate / probe
+  __shared__ unsigned short wl_sorted[kSlab];  // work list: local query ids, cheapest cost class first
+  __shared__ int s_cnt[kCostClasses][kWarps];
+  __shared__ int s_base[kCostClasses][kWarps];
+  __shared__ int s_total;
   const ScanTask& t = tasks[blockIdx.y];
-  const int ncta = (t.n + kSweepThreads * QPT - 1) / (kSweepThreads * QPT);
+  const int ncta = (t.n + kSlab - 1) / kSlab;
   if ((int)blockIdx.x >= ncta) return;
   IcpState* st = t.state;
   if (threadIdx.x < 16) sT[threadIdx.x] = st->Tinc[threadIdx.x];
@@ -84,41 +101,142 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) icp_sweep_p2p(co
   __syncthreads();
   if (s_flags[0]) return;
   const bool first = s_flags[1] == 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int base = blockIdx.x * kSlab;
+  const float margin = cfg.margin_frac * t.grid.cell;
 
+  // ---- phase A
+  unsigned packed = 0;  // 4 bits per slab: cost class of this thread's query, 15 = no search needed
+  int mycnt = 0;        // lane c < kCostClasses: entries of class c in this warp
+#pragma unroll 1
+  for (int qi = 0; qi < QPT; ++qi) {
+    const int i = base + qi * kSweepThreads + threadIdx.x;
+    int cls = 15;
+    if (i < t.n) {
+      const float4 p = first ? __ldg(t.src + i) : t.cur[i];
+      const float4 q = xform_f(sT, p.x, p.y, p.z);
+      t.cur[i] = q;
+      float seed = INFINITY;
+      bool need = false;
+      if (!(isfinite(q.x) && isfinite(q.y) && isfinite(q.z))) {
+        atomicOr(&st->pad, 1);  // non-finite source point or transform: reported by the last CTA
+        t.corr_idx[i] = -1;
+        t.corr_d2[i] = INFINITY;
+        t.cand[i] = make_int2(-1, -1);
+        t.lb[i] = 0.0f;
+      } else if (first) {
+        need = true;
+        seed = probe_seed(t.grid, q.x, q.y, q.z);
+      } else {
+        int2 c = t.cand[i];
+        // bound after this iteration's motion (upper-rounded step, lower-rounded difference)
+        const float step = __fmul_ru(__fsqrt_ru(sqdist3(q.x, q.y, q.z, p.x, p.y, p.z)), kRelUp);
+        const float L = __fsub_rd(t.lb[i], step);
+        unsigned long long k0 = kInfKey, k1 = kInfKey;
+        if (c.x >= 0) {
+          const float4 m = __ldg(t.grid.pts + c.x);
+          k0 = pack_key(sqdist3(q.x, q.y, q.z, m.x, m.y, m.z), __float_as_int(m.w));
+        }
+        if (c.y >= 0) {
+          const float4 m = __ldg(t.grid.pts + c.y);
+          k1 = pack_key(sqdist3(q.x, q.y, q.z, m.x, m.y, m.z), __float_as_int(m.w));
+        }
+        if (k1 < k0) {  // keep cand.x = the nearer of the two
+          k0 = k1;
+          c = make_int2(c.y, c.x);
+          t.cand[i] = c;
+        }
+        const float d2 = key_d2(k0);
+        const float L2 = L > 0.0f ? __fmul_rd(__fmul_rd(L, L), kRelDown) : 0.0f;
+        if (fminf(d2, cfg.bound2) < L2) {  // certificate holds: the NN is cand.x, or nothing is within the bound
+          const bool keep = (d2 < L2) && !((double)d2 > cfg.max2);
+          t.corr_idx[i] = keep ? key_idx(k0) : -1;
+          t.corr_d2[i] = d2;
+          t.lb[i] = L;
+        } else {
+          need = true;
+          seed = d2;
+        }
+      }
+      if (need) {
+        wl_thr[qi * kSweepThreads + threadIdx.x] = seed;
+        cls = cost_class(cell_box(t.grid, q.x, q.y, q.z, seed, cfg.bound2, margin, cfg.max_rings));
+      }
+    }
+    packed |= (unsigned)cls << (4 * qi);
+#pragma unroll
+    for (int c = 0; c < kCostClasses; ++c) {
+      const unsigned bal = __ballot_sync(0xFFFFFFFFu, cls == c);
+      if (lane == c) mycnt += __popc(bal);
+    }
+  }
+  if (lane < kCostClasses) s_cnt[lane][warp] = mycnt;
+  __syncthreads();
+  if (threadIdx.x < kCostClasses * kWarps) {  // exclusive prefix over (class, warp), class-major
+    const int c = threadIdx.x / kWarps, w = threadIdx.x % kWarps;
+    int b = 0;
+    for (int k = 0; k < c * kWarps + w; ++k) b += s_cnt[k / kWarps][k % kWarps];
+    s_base[c][w] = b;
+    if (threadIdx.x == kCostClasses * kWarps - 1) s_total = b + s_cnt[c][w];
+  }
+  __syncthreads();
+  {
+    int run[kCostClasses];
+#pragma unroll
+    for (int c = 0; c < kCostClasses; ++c) run[c] = s_base[c][warp];
+#pragma unroll 1
+    for (int qi = 0; qi < QPT; ++qi) {
+      const int cls = (packed >> (4 * qi)) & 15;
+#pragma unroll
+      for (int c = 0; c < kCostClasses; ++c) {
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, cls == c);
+        if (cls == c) wl_sorted[run[c] + __popc(bal & lt_mask)] = (unsigned short)(qi * kSweepThreads + threadIdx.x);
+        run[c] += __popc(bal);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase B
+  const int total = s_total;
+  for (int e = threadIdx.x; e < total; e += kSweepThreads) {
+    const int loc = wl_sorted[e];
+    const int i = base + loc;
+    const float4 q = t.cur[i];
+    const CellBox bx = cell_box(t.grid, q.x, q.y, q.z, wl_thr[loc], cfg.bound2, margin, cfg.max_rings);
+    Top3 top;
+    float lrest;
+    box_search<kSweepThreads>(t.grid, q.x, q.y, q.z, bx, sc, top, lrest);
+    const float d2 = key_d2(top.k0);
+    const bool keep = (top.k0 != kInfKey) && !((double)d2 > cfg.max2);
+    t.corr_idx[i] = keep ? key_idx(top.k0) : -1;
+    t.corr_d2[i] = d2;
+    t.cand[i] = make_int2(top.p0, top.p1);
+    t.lb[i] = top3_bound(top, lrest);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && total) atomicAdd(&st->unresolved, (unsigned int)total);
+
+  // ---- phase C
   double acc[kNumSums];
 #pragma unroll
   for (int c = 0; c < kNumSums; ++c) acc[c] = 0.0;
-
 #pragma unroll 1
   for (int qi = 0; qi < QPT; ++qi) {
-    const int i = (blockIdx.x * QPT + qi) * kSweepThreads + threadIdx.x;
+    const int i = base + qi * kSweepThreads + threadIdx.x;
     if (i >= t.n) break;
-    const float4 p = first ? __ldg(t.src + i) : t.cur[i];
-    const float4 q = xform_f(sT, p.x, p.y, p.z);
-    t.cur[i] = q;
-    NNResult r;
-    r.key = kInfKey;
-    r.pos = -1;
-    if (isfinite(q.x) && isfinite(q.y) && isfinite(q.z))
-      r = grid_nn<kSweepThreads>(t.grid, q.x, q.y, q.z, cfg.bound2, cfg.max_rings, first ? -1 : t.corr_pos[i], sc);
-    else
-      atomicOr(&st->pad, 1);  // non-finite source point or transform: reported by the last CTA
-    const float d2 = key_d2(r.key);
-    const bool keep = (r.key != kInfKey) && !((double)d2 > cfg.max2);
-    t.corr_idx[i] = keep ? key_idx(r.key) : -1;
-    t.corr_d2[i] = d2;
-    t.corr_pos[i] = r.pos;
-    if (keep) {
-      const float4 m = __ldg(t.grid.pts + r.pos);
-      const double sx = q.x, sy = q.y, sz = q.z, dx = m.x, dy = m.y, dz = m.z;
-      acc[0] += 1.0;
-      acc[1] += sx; acc[2] += sy; acc[3] += sz;
-      acc[4] += dx; acc[5] += dy; acc[6] += dz;
-      acc[7] += dx * sx; acc[8] += dx * sy; acc[9] += dx * sz;
-      acc[10] += dy * sx; acc[11] += dy * sy; acc[12] += dy * sz;
-      acc[13] += dz * sx; acc[14] += dz * sy; acc[15] += dz * sz;
-      acc[16] += (double)d2;
-    }
+    if (t.corr_idx[i] < 0) continue;
+    const float4 q = t.cur[i];
+    const float4 m = __ldg(t.grid.pts + t.cand[i].x);
+    const double sx = q.x, sy = q.y, sz = q.z, dx = m.x, dy = m.y, dz = m.z;
+    acc[0] += 1.0;
+    acc[1] += sx; acc[2] += sy; acc[3] += sz;
+    acc[4] += dx; acc[5] += dy; acc[6] += dz;
+    acc[7] += dx * sx; acc[8] += dx * sy; acc[9] += dx * sz;
+    acc[10] += dy * sx; acc[11] += dy * sy; acc[12] += dy * sz;
+    acc[13] += dz * sx; acc[14] += dz * sy; acc[15] += dz * sz;
+    acc[16] += (double)t.corr_d2[i];
   }
   cta_reduce_sums(acc, smem);
   if (!grid_reduce_last(t, smem, ncta)) return;

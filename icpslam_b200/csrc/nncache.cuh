@@ -1,0 +1,200 @@
+// nncache.cuh — exact 1-NN with a per-query certificate that lets the NEXT ICP iteration skip the search.
+//
+// Same contract as nn.cuh (it replaces pcl::KdTreeFLANN::nearestKSearch(k = 1) inside
+// CorrespondenceEstimation::determineCorrespondences, reference src/icpslam/icp_odometer.cpp:198,
+// src/icpslam/octree_mapper.cpp:114): the result is the float-arithmetic
+// nearest neighbour, ties on d2 to the smallest original index.  What is new is what the search leaves
+// behind for the query:
+//
+//   cand = (p0, p1)   sorted positions of the nearest and second-nearest target point found,
+//   L                 a lower bound on the Euclidean distance from the query to EVERY OTHER target point.
+//
+// ICP moves each query a little per iteration.  If the query has moved by `step` since the bound was
+// taken, every other point is still at least L - step away (triangle inequality), so whenever
+//       min(d(q, p0), d(q, p1))  <  L - step
+// the nearest neighbour is one of the two cached points and no search is needed (the idea of Greenspan &
+// Godin's cached-neighbour ICP, made exact in float arithmetic by the rounding margins below).  The
+// fused sweep (icp.cuh) runs that test for every query and sends only the failures here.
+//
+// The search itself: the cells overlapped by the axis-aligned box q +- r, r = sqrt(thr) + margin, where
+// thr is the squared distance of the best cached candidate (or of the own-cell / first-ring probe when
+// there is none).  Cells are ordered x-fastest, so each (y, z) row of the box is ONE contiguous run of
+// the sorted target array: two cell_start loads per row, no per-cell tests.  Runs are queued in shared
+// memory and scanned by one flattened loop that keeps the best key, the runner-up and the third
+// distance.  L = min(third distance, distance to the faces of the scanned box) - rounding.
+#pragma once
+#include "common.cuh"
+#include "grid.cuh"
+#include "nn.cuh"
+
+namespace b2 {
+
+constexpr float kRelUp = 1.000002f;    // > 1 + 16 ulp: turns a float distance into an upper bound
+constexpr float kRelDown = 0.999998f;  // < 1 - 16 ulp: turns a float distance into a lower bound
+
+struct Top3 {
+  unsigned long long k0;  // best (d2, original index)
+  int p0;                 // its sorted position, -1 = none
+  int p1;                 // runner-up position, -1 = none
+  float b1, b2;           // runner-up and third-best d2 (+inf = none)
+};
+
+__device__ __forceinline__ void top3_init(Top3& t) {
+  t.k0 = kInfKey;
+  t.p0 = -1;
+  t.p1 = -1;
+  t.b1 = INFINITY;
+  t.b2 = INFINITY;
+}
+
+// branch-free insertion of candidate (d, original index idx, sorted position j)
+__device__ __forceinline__ void top3_insert(Top3& t, float d, int idx, int j) {
+  const unsigned long long k = pack_key(d, idx);
+  const bool nb = k < t.k0;                   // new best
+  const float dl = nb ? key_d2(t.k0) : d;     // the loser of (candidate, old best) goes on to the runner-up test
+  const int pl = nb ? t.p0 : j;
+  t.k0 = nb ? k : t.k0;
+  t.p0 = nb ? j : t.p0;
+  const bool ns = dl < t.b1;                  // new runner-up
+  t.b2 = ns ? t.b1 : fminf(t.b2, dl);
+  t.p1 = ns ? pl : t.p1;
+  t.b1 = ns ? dl : t.b1;
+}
+
+// min d2 over one run of the sorted array (probe only: no candidate bookkeeping)
+__device__ __forceinline__ float probe_run(const float4* __restrict__ pts, int s, int e, float qx, float qy, float qz,
+                                           float best) {
+#pragma unroll 2
+  for (int j = s; j < e; ++j) {
+    const float4 p = __ldg(pts + j);
+    best = fminf(best, sqdist3(qx, qy, qz, p.x, p.y, p.z));
+  }
+  return best;
+}
+
+struct CellBox {
+  int xa, xb, ya, yb, za, zb;
+};
+
+// First-touch probe (no cached candidate): min d2 over the own cell, then over the 3x3x3 block (nine
+// x-runs), so that the real scan starts from a finite radius.
+__device__ __forceinline__ float probe_seed(const GridView& g, float qx, float qy, float qz) {
+  const int cx = cell_coord(qx, g.ox, g.inv_cell, g.nx);
+  const int cy = cell_coord(qy, g.oy, g.inv_cell, g.ny);
+  const int cz = cell_coord(qz, g.oz, g.inv_cell, g.nz);
+  const int* cs = g.cell_start + (cz * g.ny + cy) * g.nx + cx;
+  float thr = probe_run(g.pts, __ldg(cs), __ldg(cs + 1), qx, qy, qz, INFINITY);
+  if (!(thr < INFINITY)) {
+    const int xa = max(cx - 1, 0), xb = min(cx + 1, g.nx - 1);
+    for (int z = max(cz - 1, 0); z <= min(cz + 1, g.nz - 1); ++z)
+      for (int y = max(cy - 1, 0); y <= min(cy + 1, g.ny - 1); ++y) {
+        const int* row = g.cell_start + (z * g.ny + y) * g.nx;
+        thr = probe_run(g.pts, __ldg(row + xa), __ldg(row + xb + 1), qx, qy, qz, thr);
+      }
+  }
+  return thr;
+}
+
+// The cells overlapped by the box q +- (sqrt(min(thr, bound2)) + margin), clamped to `max_span` cells
+// either side of the query's cell.  cell_coord is monotone and is the expression the build binned with,
+// so a target point within that distance of q on an axis lies in [ca, cb] on that axis.
+__device__ __forceinline__ CellBox cell_box(const GridView& g, float qx, float qy, float qz, float thr, float bound2,
+                                            float margin, int max_span) {
+  const int cx = cell_coord(qx, g.ox, g.inv_cell, g.nx);
+  const int cy = cell_coord(qy, g.oy, g.inv_cell, g.ny);
+  const int cz = cell_coord(qz, g.oz, g.inv_cell, g.nz);
+  thr = fminf(thr, bound2);
+  CellBox b;
+  if (thr < INFINITY) {
+    const float rs = __fadd_ru(__fadd_ru(__fmul_ru(__fsqrt_ru(thr), kRelUp), margin), g.slack);
+    b.xa = max(cell_coord(__fsub_rd(qx, rs), g.ox, g.inv_cell, g.nx), cx - max_span);
+    b.xb = min(cell_coord(__fadd_ru(qx, rs), g.ox, g.inv_cell, g.nx), cx + max_span);
+    b.ya = max(cell_coord(__fsub_rd(qy, rs), g.oy, g.inv_cell, g.ny), cy - max_span);
+    b.yb = min(cell_coord(__fadd_ru(qy, rs), g.oy, g.inv_cell, g.ny), cy + max_span);
+    b.za = max(cell_coord(__fsub_rd(qz, rs), g.oz, g.inv_cell, g.nz), cz - max_span);
+    b.zb = min(cell_coord(__fadd_ru(qz, rs), g.oz, g.inv_cell, g.nz), cz + max_span);
+  } else {  // unbounded search that found nothing nearby: the ring budget decides
+    b.xa = max(cx - max_span, 0); b.xb = min(cx + max_span, g.nx - 1);
+    b.ya = max(cy - max_span, 0); b.yb = min(cy + max_span, g.ny - 1);
+    b.za = max(cz - max_span, 0); b.zb = min(cz + max_span, g.nz - 1);
+  }
+  return b;
+}
+
+// Cost class of a box search (how many cells it will visit): queries of one class are searched by the
+// same warps, so that a warp's run time (its slowest lane) is close to its lanes' mean.
+constexpr int kCostClasses = 6;
+__device__ __forceinline__ int cost_class(const CellBox& b) {
+  const int cells = (b.xb - b.xa + 1) * (b.yb - b.ya + 1) * (b.zb - b.za + 1);
+  return cells <= 1 ? 0 : cells <= 2 ? 1 : cells <= 4 ? 2 : cells <= 8 ? 3 : cells <= 27 ? 4 : 5;
+}
+
+// Exact nearest / second nearest over the cells of `b`.  On return `lrest` is a lower bound on the
+// distance from q to every target point that was NOT scanned (those outside the box).
+template <int THREADS>
+__device__ __forceinline__ void box_search(const GridView& g, float qx, float qy, float qz, const CellBox& b,
+                                           NNScratch<THREADS>& sc, Top3& top, float& lrest) {
+  top3_init(top);
+  const int tid = threadIdx.x;
+  const int xa = b.xa, xb = b.xb, ya = b.ya, yb = b.yb, za = b.za, zb = b.zb;
+  // distance from q to the outside of the box (faces that have cells beyond them only)
+  {
+    float gmin = INFINITY;
+    if (xa > 0) gmin = fminf(gmin, __fsub_rd(qx, __fadd_ru(g.ox, __fmul_ru((float)xa, g.cell))));
+    if (xb < g.nx - 1) gmin = fminf(gmin, __fsub_rd(__fadd_rd(g.ox, __fmul_rd((float)(xb + 1), g.cell)), qx));
+    if (ya > 0) gmin = fminf(gmin, __fsub_rd(qy, __fadd_ru(g.oy, __fmul_ru((float)ya, g.cell))));
+    if (yb < g.ny - 1) gmin = fminf(gmin, __fsub_rd(__fadd_rd(g.oy, __fmul_rd((float)(yb + 1), g.cell)), qy));
+    if (za > 0) gmin = fminf(gmin, __fsub_rd(qz, __fadd_ru(g.oz, __fmul_ru((float)za, g.cell))));
+    if (zb < g.nz - 1) gmin = fminf(gmin, __fsub_rd(__fadd_rd(g.oz, __fmul_rd((float)(zb + 1), g.cell)), qz));
+    lrest = fmaxf(__fsub_rd(gmin, g.slack), 0.0f);
+  }
+  // rows of the box -> runs -> one flattened scan per chunk of kListCap runs
+  const int nrow = (yb - ya + 1) * (zb - za + 1);
+  int y = ya, z = za;
+  for (int k = 0; k < nrow;) {
+    int nlist = 0;
+#pragma unroll 2
+    for (; k < nrow && nlist < kListCap; ++k) {
+      const int* row = g.cell_start + (z * g.ny + y) * g.nx;
+      const int s = __ldg(row + xa), e = __ldg(row + xb + 1);
+      if (++y > yb) {
+        y = ya;
+        ++z;
+      }
+      if (e > s) {
+        sc.start[nlist][tid] = s;
+        sc.meta[nlist][tid] = (unsigned)e;
+        ++nlist;
+      }
+    }
+    int li = 0, j = 0, e = 0;
+    for (;;) {
+      if (j >= e) {
+        if (li >= nlist) break;
+        j = sc.start[li][tid];
+        e = (int)sc.meta[li][tid];
+        ++li;
+      }
+      // two candidates per trip, both loads in flight before either is used
+      const bool two = j + 1 < e;
+      const float4 p = __ldg(g.pts + j);
+      const float4 p1 = __ldg(g.pts + (two ? j + 1 : j));
+      const float d = sqdist3(qx, qy, qz, p.x, p.y, p.z);
+      const float d1 = two ? sqdist3(qx, qy, qz, p1.x, p1.y, p1.z) : INFINITY;
+      // only candidates that beat the third-best distance (or tie the best) can change the state
+      if (fminf(d, d1) < top.b2 || fminf(d, d1) <= key_d2(top.k0)) {
+        top3_insert(top, d, __float_as_int(p.w), j);
+        if (two) top3_insert(top, d1, __float_as_int(p1.w), j + 1);
+      }
+      j += 2;
+    }
+  }
+}
+
+// lower bound on the distance to every target point other than top.p0 / top.p1
+__device__ __forceinline__ float top3_bound(const Top3& top, float lrest) {
+  const float l3 = top.b2 < INFINITY ? __fmul_rd(__fsqrt_rd(top.b2), kRelDown) : INFINITY;
+  return fminf(l3, lrest);
+}
+
+}  // namespace b2

@@ -82,7 +82,7 @@ class Timing(C.Structure):
         ("build_ms", C.c_double),
         ("total_ms", C.c_double),
         ("kernel_launches", C.c_int64),
-        ("reserved2", C.c_uint64),
+        ("nn_searches", C.c_uint64),
     ]
 
 

@@ -102,7 +102,8 @@ typedef struct b2icp_timing {
   double build_ms;           /* reserved */
   double total_ms;           /* first launch -> last launch, CUDA events */
   int64_t kernel_launches;   /* every kernel this handle has launched since b2icp_create (always filled) */
-  uint64_t reserved2;
+  uint64_t nn_searches;      /* queries of those launches that needed a real neighbour search (the rest were
+                              * settled by their cached-neighbour certificate, nncache.cuh) */
 } b2icp_timing;
 
 /* Fill `p` with the reference's constants for one of its two call sites. */
