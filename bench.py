@@ -232,6 +232,7 @@ def main():
     ap.add_argument("--impl", default="b2icp", choices=["b2icp", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=4, help="sweeps timed on the CPU oracle (rank 0, N=1)")
     ap.add_argument("--grid-cell", type=float, default=0.0, help="neighbour-grid cell edge in metres (0 = auto); tuning only")
+    ap.add_argument("--presort", type=float, default=0.0, help="EXPERIMENT: pre-sort every sweep by cell of this edge (m)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b2icp" else args.warmup
 
@@ -267,6 +268,12 @@ def main():
     else:
         map_xyzw, sweeps = load_workload(rank * args.batch, args.batch)
 
+    if args.presort > 0:
+        o = map_xyzw[:, :3].min(axis=0)
+        def _sort(s):
+            c = np.floor((s[:, :3] - o) / args.presort).astype(np.int64)
+            return np.ascontiguousarray(s[np.lexsort((c[:, 0], c[:, 1], c[:, 2]))])
+        sweeps = [_sort(s) for s in sweeps]
     stream = torch.cuda.current_stream()
     reg = R.Registration(preset=R.PRESET_MAPPER, device=local_rank, profile=1, grid_cell=args.grid_cell)
     reg.setStream(stream.cuda_stream)

@@ -93,11 +93,11 @@ struct GridSlot {
 
 struct ScanSlot {
   Cloud src;
-  DeviceBuf cur, corr_idx, corr_d2, corr_pos, cand, lb, partials;
+  DeviceBuf cur, corr_idx, corr_d2, corr_pos, c0, c1, lb, partials;
   DeviceBuf cov, mahal, gicp_partials;  // GICP: source covariances, Mahalanobis matrices, per-CTA sums
   int grid = 0;
   void release() {
-    for (DeviceBuf* b : {&src.raw, &cur, &corr_idx, &corr_d2, &corr_pos, &cand, &lb, &partials, &cov, &mahal, &gicp_partials})
+    for (DeviceBuf* b : {&src.raw, &cur, &corr_idx, &corr_d2, &corr_pos, &c0, &c1, &lb, &partials, &cov, &mahal, &gicp_partials})
       b->release();
   }
 };
@@ -340,12 +340,13 @@ int set_target_impl(b2icp_handle* h, int gi, const float* xyzw, size_t n, bool f
 
 int ensure_slot_work(b2icp_handle* h, ScanSlot& s) {
   const size_t n = s.src.n;
-  const size_t ncta = (n + kSweepThreads - 1) / kSweepThreads;
+  const size_t ncta = (n + 31) / 32;  // per-warp partial sums, worst case one 32-query slab per warp
   CK(s.cur.ensure(n * sizeof(float4)));
   CK(s.corr_idx.ensure(n * sizeof(int)));
   CK(s.corr_d2.ensure(n * sizeof(float)));
   CK(s.corr_pos.ensure(n * sizeof(int)));
-  CK(s.cand.ensure(n * sizeof(int2)));
+  CK(s.c0.ensure(n * sizeof(float4)));
+  CK(s.c1.ensure(n * sizeof(float4)));
   CK(s.lb.ensure(n * sizeof(float)));
   CK(s.partials.ensure(ncta * kNumSums * sizeof(double)));
   return B2ICP_OK;
@@ -388,7 +389,8 @@ int run_batch(b2icp_handle* h, int B, const float* guesses) {
     t.corr_idx = s.corr_idx.as<int>();
     t.corr_d2 = s.corr_d2.as<float>();
     t.corr_pos = s.corr_pos.as<int>();
-    t.cand = s.cand.as<int2>();
+    t.c0 = s.c0.as<float4>();
+    t.c1 = s.c1.as<float4>();
     t.lb = s.lb.as<float>();
     t.partials = s.partials.as<double>();
     t.state = h->states.as<IcpState>() + i;
@@ -418,11 +420,13 @@ int run_batch(b2icp_handle* h, int B, const float* guesses) {
     }
     CK(cudaEventRecord(h->events[0], h->stream));
   }
-  // queries per thread: amortise prologue / reduction / barrier when there is enough work to keep
-  // every SM's resident CTA slots full for at least two waves
+  // queries per lane (a warp owns 32 * qpt consecutive queries): long slabs amortise the reduction and keep
+  // the lanes of the search phase busy; short ones are for launches that could not fill the SMs otherwise
+  // (measured on B200, 32 x 64k sweeps: qpt 2 -> 144 us, 4 -> 113 us, 8 -> 109 us per iteration)
   auto ctas_at = [&](int qpt) { return (long long)B * (long long)((max_n + (size_t)kSweepThreads * qpt - 1) / ((size_t)kSweepThreads * qpt)); };
   const long long want = 2LL * 148 * kSweepMinCtas;
-  const int qpt = h->qpt_override > 0 ? h->qpt_override : (ctas_at(4) >= want ? 4 : (ctas_at(2) >= want ? 2 : 1));
+  const int qpt = h->qpt_override > 0 ? h->qpt_override
+                                      : (ctas_at(8) >= want ? 8 : (ctas_at(4) >= want ? 4 : (ctas_at(2) >= want ? 2 : 1)));
   dim3 grid((unsigned)((max_n + (size_t)kSweepThreads * qpt - 1) / ((size_t)kSweepThreads * qpt)), (unsigned)B, 1);
   for (int it = 0; it < iters; ++it) {
     if (prof) CK(cudaEventRecord(h->events[2 + 2 * it], h->stream));
@@ -436,7 +440,11 @@ int run_batch(b2icp_handle* h, int B, const float* guesses) {
       icp_sweep_p2p<1><<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>(), h->cfg);
     if (prof) CK(cudaEventRecord(h->events[3 + 2 * it], h->stream));
   }
-  h->launches += iters;
+  {  // correspondences of the last sweep, for b2icp_get_correspondences
+    const dim3 fgrid((unsigned)((max_n + 255) / 256), (unsigned)B, 1);
+    icp_finalize_corr<<<fgrid, 256, 0, h->stream>>>(h->tasks.as<ScanTask>(), h->cfg);
+  }
+  h->launches += iters + 1;
   if (prof) CK(cudaEventRecord(h->events[1], h->stream));
   h->last_batch = B;
   return B2ICP_OK;

@@ -14,8 +14,12 @@ namespace b2 {
 #define B2_SWEEP_THREADS 256
 #endif
 #ifndef B2_SWEEP_MIN_CTAS
-#define B2_SWEEP_MIN_CTAS 4
+#define B2_SWEEP_MIN_CTAS 3
 #endif
+#ifndef B2_PHASE_A_UNROLL
+#define B2_PHASE_A_UNROLL 1
+#endif
+constexpr int kPhaseAUnroll = B2_PHASE_A_UNROLL;
 constexpr int kSweepThreads = B2_SWEEP_THREADS;    // CTA size of the fused sweep kernels
 constexpr int kSweepMinCtas = B2_SWEEP_MIN_CTAS;   // resident CTAs per SM the sweep is compiled for
 constexpr int kNumSums = 17;         // n, sum(src)[3], sum(dst)[3], sum(dst*src^T)[9], sum(d2)
@@ -48,7 +52,7 @@ struct IcpState {
   int n_corr;        // gated correspondences of the last sweep
   unsigned int ticket;   // last-CTA election counter
   unsigned int unresolved;  // P2P loop: queries that needed a real search, summed over the iterations
-  int pad;
+  int pad;           // set to 1 by a sweep thread that met a non-finite coordinate
 };
 
 struct IcpConfig {
@@ -72,13 +76,21 @@ struct ScanTask {
   int* corr_idx;       // [n] target index of the last sweep, -1 = gated out
   float* corr_d2;      // [n] float d2 of the last sweep
   int* corr_pos;       // [n] sorted-array position of the last match (seed of the next search), -1 = none
-  int2* cand;          // [n] sorted positions of the nearest / second-nearest target point (nncache.cuh), -1 = none
-  float* lb;           // [n] lower bound on the distance from cur[i] to every target point not in cand[i]
-  double* partials;    // [gridDim.x][kNumSums] per-CTA sums
+  float4* c0;          // [n] nearest target point found for cur[i]: xyz + original index (int bits, -1 = none)
+  float4* c1;          // [n] runner-up, same layout (nncache.cuh)
+  float* lb;           // [n] lower bound on the distance from cur[i] to every target point other than c0, c1
+  double* partials;    // [ceil(n / 32)][kNumSums] per-warp sums of one sweep
   IcpState* state;
   int n;
   int pad;
 };
+
+// Per-query state is streamed once per iteration and is larger than what the L2 can keep next to the
+// target cloud and its cell table: evict-first accesses keep it from pushing those out.
+template <class T>
+__device__ __forceinline__ T ld_stream(const T* p) { return __ldcs(p); }
+template <class T>
+__device__ __forceinline__ void st_stream(T* p, const T& v) { __stcs(p, v); }
 
 __device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
 __device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }

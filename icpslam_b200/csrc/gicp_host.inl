@@ -596,7 +596,8 @@ int run_gicp(b2icp_handle* h, const float* guess16) {
   t.corr_idx = s.corr_idx.as<int>();
   t.corr_d2 = s.corr_d2.as<float>();
   t.corr_pos = s.corr_pos.as<int>();
-  t.cand = s.cand.as<int2>();
+  t.c0 = s.c0.as<float4>();
+  t.c1 = s.c1.as<float4>();
   t.lb = s.lb.as<float>();
   t.partials = s.partials.as<double>();
   t.state = h->states.as<IcpState>();

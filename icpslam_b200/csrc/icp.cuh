@@ -20,230 +20,193 @@
 
 namespace b2 {
 
-// Sum `acc[kNumSums]` over the CTA in a fixed order; result valid in warp 0 lane 0's acc.
-__device__ __forceinline__ void cta_reduce_sums(double* acc, double (*smem)[kNumSums]) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int c = 0; c < kNumSums; ++c) acc[c] = warp_sum(acc[c]);
-  if (lane == 0) {
-#pragma unroll
-    for (int c = 0; c < kNumSums; ++c) smem[warp][c] = acc[c];
-  }
-  __syncthreads();
-  if (warp == 0) {
-    if (lane < kNumSums) {
-      double s = 0;
-#pragma unroll
-      for (int w = 0; w < kSweepThreads / 32; ++w) s += smem[w][lane];
-      smem[0][lane] = s;
-    }
-  }
-  __syncthreads();
+__device__ __forceinline__ void accumulate_pair(double* acc, const float4& q, const float4& m, float d2) {
+  const double sx = q.x, sy = q.y, sz = q.z, dx = m.x, dy = m.y, dz = m.z;
+  acc[0] += 1.0;
+  acc[1] += sx; acc[2] += sy; acc[3] += sz;
+  acc[4] += dx; acc[5] += dy; acc[6] += dz;
+  acc[7] += dx * sx; acc[8] += dx * sy; acc[9] += dx * sz;
+  acc[10] += dy * sx; acc[11] += dy * sy; acc[12] += dy * sz;
+  acc[13] += dz * sx; acc[14] += dz * sy; acc[15] += dz * sz;
+  acc[16] += (double)d2;
 }
 
-// Called by every thread of every CTA after cta_reduce_sums; returns true in ALL threads of the last
-// CTA to arrive (for this scan), with the grid-wide sums left in smem[0][0..kNumSums).
-__device__ __forceinline__ bool grid_reduce_last(const ScanTask& t, double (*smem)[kNumSums], int ncta) {
-  __shared__ unsigned int s_ticket;
-  if (threadIdx.x < kNumSums) t.partials[(size_t)blockIdx.x * kNumSums + threadIdx.x] = smem[0][threadIdx.x];
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_ticket = atomicAdd(&t.state->ticket, 1u);
-  __syncthreads();
-  if (s_ticket != (unsigned int)(ncta - 1)) return false;
-  __threadfence();
-  // fixed-order reduction over CTAs: thread j sums CTAs j, j+256, ... then the CTA-wide fixed tree
-  double acc[kNumSums];
-#pragma unroll
-  for (int c = 0; c < kNumSums; ++c) acc[c] = 0.0;
-  for (int b = threadIdx.x; b < ncta; b += kSweepThreads) {
-    const double* p = t.partials + (size_t)b * kNumSums;
-#pragma unroll
-    for (int c = 0; c < kNumSums; ++c) acc[c] += __ldcg(p + c);
-  }
-  __syncthreads();
-  cta_reduce_sums(acc, smem);
-  return true;
-}
-
-// QPT = queries per thread: consecutive 256-point slabs handled by the same CTA, so that the prologue,
-// the 17-value fp64 reduction and the CTA barriers are paid once per QPT queries, and so that the
-// compacted list of queries that need a real search is long enough to fill the CTA's warps.
+// One ICP iteration = one launch over all scans of the batch (nncache.cuh explains the certificate).
 //
-// Three phases per CTA (nncache.cuh explains the certificate):
-//   A  every query: q = T_inc * q (in place), distances to its two cached candidates, certificate
-//      test; passers get their correspondence at once, the others are compacted (ballot + prefix, so
-//      the list order is deterministic) into a shared-memory work list;
-//   B  the work list, one entry per thread: exact box search, new candidates + bound;
-//   C  every query again, in (thread, slab) order: the 17 fp64 sums from the stored correspondences —
-//      the summation order does not depend on which queries were searched, so results are
-//      bit-reproducible, and the 34 accumulator registers are not live during the search.
+// Per-query state carried between iterations (ScanTask): cur (running cloud), c0 / c1 (nearest and
+// runner-up target point: xyz + original index in .w, index -1 = none), lb (distance bound).  All of it
+// is read and written with coalesced, evict-first 16-byte accesses; nothing in the streaming pass depends
+// on a gathered load.  corr_idx / corr_d2 are produced once, after the loop (icp_finalize_corr).
+//
+// The unit of work is a WARP and its slab of 32 * QPT consecutive queries; warps never wait for each
+// other (no CTA barrier anywhere), so the scheduler always has warps in different phases to pick from:
+//   A  every query of the slab, 32 at a time: q = T_inc * q (in place), distances to its two cached
+//      candidates, certificate test.  Passers add their pair to the lane's 17 fp64 sums at once; the
+//      others are compacted (ballot + popc: the order is a function of the data only) into the warp's
+//      work list in shared memory;
+//   B  the work list, one entry per lane: exact box search, new candidates + bound, pair added to the
+//      sums of the lane that searched it;
+//   C  xor-butterfly over the lanes -> partials[slab]; the last warp of the scan (atomic ticket) adds the
+//      slabs' partials in a fixed order and runs Umeyama + the convergence test (solve.cuh).
+// Which lane sums which pair depends only on the data and every reduction has a fixed order, so results
+// are bit-reproducible from run to run.
 template <int QPT>
 __global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) icp_sweep_p2p(const ScanTask* __restrict__ tasks, IcpConfig cfg) {
   constexpr int kWarps = kSweepThreads / 32;
-  constexpr int kSlab = QPT * kSweepThreads;  // queries per CTA
-  __shared__ double smem[kWarps][kNumSums];
-  __shared__ NNScratch<kSweepThreads> sc;
-  __shared__ float sT[16];
-  __shared__ int s_flags[2];
-  __shared__ float wl_thr[kSlab];            // per local query: squared distance of its best cached candidate / probe
-  __shared__ unsigned short wl_sorted[kSlab];  // work list: local query ids, cheapest cost class first
-  __shared__ int s_cnt[kCostClasses][kWarps];
-  __shared__ int s_base[kCostClasses][kWarps];
-  __shared__ int s_total;
+  constexpr int kWarpSlab = 32 * QPT;
+  __shared__ NNScratch<kSweepThreads> sc;             // one column per thread: private to its warp by construction
+  __shared__ float sT[kWarps][16];
+  __shared__ unsigned short wl_id[kWarps][kWarpSlab];  // work list of the warp: query index inside its slab
+  __shared__ float wl_thr[kWarps][kWarpSlab];          // squared distance of the best cached candidate (+inf: none)
   const ScanTask& t = tasks[blockIdx.y];
-  const int ncta = (t.n + kSlab - 1) / kSlab;
-  if ((int)blockIdx.x >= ncta) return;
-  IcpState* st = t.state;
-  if (threadIdx.x < 16) sT[threadIdx.x] = st->Tinc[threadIdx.x];
-  if (threadIdx.x == 16) s_flags[0] = st->done;
-  if (threadIdx.x == 17) s_flags[1] = st->iter;
-  __syncthreads();
-  if (s_flags[0]) return;
-  const bool first = s_flags[1] == 0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned lt_mask = (1u << lane) - 1u;
-  const int base = blockIdx.x * kSlab;
+  const int nslab = (t.n + kWarpSlab - 1) / kWarpSlab;
+  const int slab = blockIdx.x * kWarps + warp;
+  if (slab >= nslab) return;
+  IcpState* st = t.state;
+  if (st->done) return;
+  const bool first = st->iter == 0;
+  if (lane < 16) sT[warp][lane] = st->Tinc[lane];
+  __syncwarp();
+  const float* T = sT[warp];
+  const int base = slab * kWarpSlab;
   const float margin = cfg.margin_frac * t.grid.cell;
 
+  double acc[kNumSums];
+#pragma unroll
+  for (int c = 0; c < kNumSums; ++c) acc[c] = 0.0;
+
   // ---- phase A
-  unsigned packed = 0;  // 4 bits per slab: cost class of this thread's query, 15 = no search needed
-  int mycnt = 0;        // lane c < kCostClasses: entries of class c in this warp
-#pragma unroll 1
+  int wc = 0;  // entries in the warp's work list (warp-uniform)
+#pragma unroll kPhaseAUnroll
   for (int qi = 0; qi < QPT; ++qi) {
-    const int i = base + qi * kSweepThreads + threadIdx.x;
-    int cls = 15;
+    const int i = base + qi * 32 + lane;
+    bool need = false;
+    float seed = INFINITY;
     if (i < t.n) {
-      const float4 p = first ? __ldg(t.src + i) : t.cur[i];
-      const float4 q = xform_f(sT, p.x, p.y, p.z);
-      t.cur[i] = q;
-      float seed = INFINITY;
-      bool need = false;
+      float4 p, c0, c1;
+      float lb = 0.0f;
+      if (first) {
+        p = __ldg(t.src + i);
+      } else {  // four independent coalesced loads
+        p = ld_stream(t.cur + i);
+        c0 = ld_stream(t.c0 + i);
+        c1 = ld_stream(t.c1 + i);
+        lb = ld_stream(t.lb + i);
+      }
+      const float4 q = xform_f(T, p.x, p.y, p.z);
+      st_stream(t.cur + i, q);
       if (!(isfinite(q.x) && isfinite(q.y) && isfinite(q.z))) {
-        atomicOr(&st->pad, 1);  // non-finite source point or transform: reported by the last CTA
-        t.corr_idx[i] = -1;
-        t.corr_d2[i] = INFINITY;
-        t.cand[i] = make_int2(-1, -1);
+        atomicOr(&st->pad, 1);  // non-finite source point or transform: reported by the last warp
+        t.c0[i] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+        t.c1[i] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
         t.lb[i] = 0.0f;
       } else if (first) {
         need = true;
-        seed = probe_seed(t.grid, q.x, q.y, q.z);
       } else {
-        int2 c = t.cand[i];
         // bound after this iteration's motion (upper-rounded step, lower-rounded difference)
-        const float step = __fmul_ru(__fsqrt_ru(sqdist3(q.x, q.y, q.z, p.x, p.y, p.z)), kRelUp);
-        const float L = __fsub_rd(t.lb[i], step);
-        unsigned long long k0 = kInfKey, k1 = kInfKey;
-        if (c.x >= 0) {
-          const float4 m = __ldg(t.grid.pts + c.x);
-          k0 = pack_key(sqdist3(q.x, q.y, q.z, m.x, m.y, m.z), __float_as_int(m.w));
-        }
-        if (c.y >= 0) {
-          const float4 m = __ldg(t.grid.pts + c.y);
-          k1 = pack_key(sqdist3(q.x, q.y, q.z, m.x, m.y, m.z), __float_as_int(m.w));
-        }
-        if (k1 < k0) {  // keep cand.x = the nearer of the two
+        const float step = __fmul_ru(sqrt_fast(sqdist3(q.x, q.y, q.z, p.x, p.y, p.z)), kRelUp);
+        const float L = __fsub_rd(lb, step);
+        const int i0 = __float_as_int(c0.w), i1 = __float_as_int(c1.w);
+        unsigned long long k0 = i0 >= 0 ? pack_key(sqdist3(q.x, q.y, q.z, c0.x, c0.y, c0.z), i0) : kInfKey;
+        const unsigned long long k1 = i1 >= 0 ? pack_key(sqdist3(q.x, q.y, q.z, c1.x, c1.y, c1.z), i1) : kInfKey;
+        if (k1 < k0) {  // keep c0 = the nearer of the two
           k0 = k1;
-          c = make_int2(c.y, c.x);
-          t.cand[i] = c;
+          st_stream(t.c0 + i, c1);
+          st_stream(t.c1 + i, c0);
+          c0 = c1;
         }
         const float d2 = key_d2(k0);
         const float L2 = L > 0.0f ? __fmul_rd(__fmul_rd(L, L), kRelDown) : 0.0f;
-        if (fminf(d2, cfg.bound2) < L2) {  // certificate holds: the NN is cand.x, or nothing is within the bound
-          const bool keep = (d2 < L2) && !((double)d2 > cfg.max2);
-          t.corr_idx[i] = keep ? key_idx(k0) : -1;
-          t.corr_d2[i] = d2;
-          t.lb[i] = L;
+        if (fminf(d2, cfg.bound2) < L2) {  // certificate holds: the NN is c0, or nothing is within the bound
+          st_stream(t.lb + i, L);
+          if ((d2 < L2) && !((double)d2 > cfg.max2)) accumulate_pair(acc, q, c0, d2);
         } else {
           need = true;
           seed = d2;
         }
       }
-      if (need) {
-        wl_thr[qi * kSweepThreads + threadIdx.x] = seed;
-        cls = cost_class(cell_box(t.grid, q.x, q.y, q.z, seed, cfg.bound2, margin, cfg.max_rings));
-      }
     }
-    packed |= (unsigned)cls << (4 * qi);
-#pragma unroll
-    for (int c = 0; c < kCostClasses; ++c) {
-      const unsigned bal = __ballot_sync(0xFFFFFFFFu, cls == c);
-      if (lane == c) mycnt += __popc(bal);
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, need);
+    if (need) {
+      const int slot = wc + __popc(bal & ((1u << lane) - 1u));
+      wl_id[warp][slot] = (unsigned short)(qi * 32 + lane);
+      wl_thr[warp][slot] = seed;
     }
+    wc += __popc(bal);
   }
-  if (lane < kCostClasses) s_cnt[lane][warp] = mycnt;
-  __syncthreads();
-  if (threadIdx.x < kCostClasses * kWarps) {  // exclusive prefix over (class, warp), class-major
-    const int c = threadIdx.x / kWarps, w = threadIdx.x % kWarps;
-    int b = 0;
-    for (int k = 0; k < c * kWarps + w; ++k) b += s_cnt[k / kWarps][k % kWarps];
-    s_base[c][w] = b;
-    if (threadIdx.x == kCostClasses * kWarps - 1) s_total = b + s_cnt[c][w];
-  }
-  __syncthreads();
-  {
-    int run[kCostClasses];
-#pragma unroll
-    for (int c = 0; c < kCostClasses; ++c) run[c] = s_base[c][warp];
-#pragma unroll 1
-    for (int qi = 0; qi < QPT; ++qi) {
-      const int cls = (packed >> (4 * qi)) & 15;
-#pragma unroll
-      for (int c = 0; c < kCostClasses; ++c) {
-        const unsigned bal = __ballot_sync(0xFFFFFFFFu, cls == c);
-        if (cls == c) wl_sorted[run[c] + __popc(bal & lt_mask)] = (unsigned short)(qi * kSweepThreads + threadIdx.x);
-        run[c] += __popc(bal);
-      }
-    }
-  }
-  __syncthreads();
+  __syncwarp();
 
   // ---- phase B
-  const int total = s_total;
-  for (int e = threadIdx.x; e < total; e += kSweepThreads) {
-    const int loc = wl_sorted[e];
-    const int i = base + loc;
+  for (int e = lane; e < wc; e += 32) {
+    const int i = base + (int)wl_id[warp][e];
     const float4 q = t.cur[i];
-    const CellBox bx = cell_box(t.grid, q.x, q.y, q.z, wl_thr[loc], cfg.bound2, margin, cfg.max_rings);
+    float seed = wl_thr[warp][e];
+    if (!(seed < INFINITY)) seed = probe_seed(t.grid, q.x, q.y, q.z);
+    const CellBox bx = cell_box(t.grid, q.x, q.y, q.z, seed, cfg.bound2, margin, cfg.max_rings);
     Top3 top;
     float lrest;
     box_search<kSweepThreads>(t.grid, q.x, q.y, q.z, bx, sc, top, lrest);
+    const float4 none = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+    const float4 m0 = top.p0 >= 0 ? __ldg(t.grid.pts + top.p0) : none;
+    st_stream(t.c0 + i, m0);
+    st_stream(t.c1 + i, top.p1 >= 0 ? __ldg(t.grid.pts + top.p1) : none);
+    st_stream(t.lb + i, top3_bound(top, lrest));
     const float d2 = key_d2(top.k0);
-    const bool keep = (top.k0 != kInfKey) && !((double)d2 > cfg.max2);
-    t.corr_idx[i] = keep ? key_idx(top.k0) : -1;
-    t.corr_d2[i] = d2;
-    t.cand[i] = make_int2(top.p0, top.p1);
-    t.lb[i] = top3_bound(top, lrest);
+    if ((top.k0 != kInfKey) && !((double)d2 > cfg.max2)) accumulate_pair(acc, q, m0, d2);
   }
-  __syncthreads();
-  if (threadIdx.x == 0 && total) atomicAdd(&st->unresolved, (unsigned int)total);
 
   // ---- phase C
-  double acc[kNumSums];
+  double mine = 0.0;  // lane c < kNumSums ends up with sum c of the slab
+#pragma unroll
+  for (int c = 0; c < kNumSums; ++c) {
+    const double s = warp_sum(acc[c]);
+    if (lane == c) mine = s;
+  }
+  if (lane < kNumSums) t.partials[(size_t)slab * kNumSums + lane] = mine;
+  __threadfence();
+  __syncwarp();
+  unsigned int ticket = 0;
+  if (lane == 0) {
+    if (wc) atomicAdd(&st->unresolved, (unsigned int)wc);
+    ticket = atomicAdd(&st->ticket, 1u);
+  }
+  ticket = __shfl_sync(0xFFFFFFFFu, ticket, 0);
+  if (ticket != (unsigned int)(nslab - 1)) return;
+  __threadfence();
+  // last warp of the scan: lane l adds slabs l, l + 32, ... in order, then the butterfly
 #pragma unroll
   for (int c = 0; c < kNumSums; ++c) acc[c] = 0.0;
-#pragma unroll 1
-  for (int qi = 0; qi < QPT; ++qi) {
-    const int i = base + qi * kSweepThreads + threadIdx.x;
-    if (i >= t.n) break;
-    if (t.corr_idx[i] < 0) continue;
-    const float4 q = t.cur[i];
-    const float4 m = __ldg(t.grid.pts + t.cand[i].x);
-    const double sx = q.x, sy = q.y, sz = q.z, dx = m.x, dy = m.y, dz = m.z;
-    acc[0] += 1.0;
-    acc[1] += sx; acc[2] += sy; acc[3] += sz;
-    acc[4] += dx; acc[5] += dy; acc[6] += dz;
-    acc[7] += dx * sx; acc[8] += dx * sy; acc[9] += dx * sz;
-    acc[10] += dy * sx; acc[11] += dy * sy; acc[12] += dy * sz;
-    acc[13] += dz * sx; acc[14] += dz * sy; acc[15] += dz * sz;
-    acc[16] += (double)t.corr_d2[i];
+  for (int b = lane; b < nslab; b += 32) {
+    const double* p = t.partials + (size_t)b * kNumSums;
+#pragma unroll
+    for (int c = 0; c < kNumSums; ++c) acc[c] += __ldcg(p + c);
   }
-  cta_reduce_sums(acc, smem);
-  if (!grid_reduce_last(t, smem, ncta)) return;
-  if (threadIdx.x == 0) {
+  __shared__ double s_sums[kWarps][kNumSums];
+#pragma unroll
+  for (int c = 0; c < kNumSums; ++c) {
+    const double s = warp_sum(acc[c]);
+    if (lane == 0) s_sums[warp][c] = s;
+  }
+  if (lane == 0) {
     st->ticket = 0;
-    p2p_finish_iteration(&smem[0][0], st, cfg);
+    p2p_finish_iteration(&s_sums[warp][0], st, cfg);
   }
+}
+
+// After the loop: the correspondences of the last sweep (what PCL's correspondences_ holds when align()
+// returns) from the per-query state: c0 is the exact nearest neighbour of cur whenever one lies within
+// the gate, so  idx = c0.idx if d2 <= max_dist^2 else -1.
+__global__ void __launch_bounds__(256) icp_finalize_corr(const ScanTask* __restrict__ tasks, IcpConfig cfg) {
+  const ScanTask& t = tasks[blockIdx.y];
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= t.n) return;
+  const float4 q = t.cur[i];
+  const float4 m = t.c0[i];
+  const int id = __float_as_int(m.w);
+  const float d2 = id >= 0 ? sqdist3(q.x, q.y, q.z, m.x, m.y, m.z) : INFINITY;
+  t.corr_idx[i] = (id >= 0 && !((double)d2 > cfg.max2)) ? id : -1;
+  t.corr_d2[i] = d2;
 }
 
 // ---- getFitnessScore(max_range): transform by final_T, exact unbounded 1-NN, mean of d2 <= range

@@ -6,12 +6,13 @@
 // nearest neighbour, ties on d2 to the smallest original index.  What is new is what the search leaves
 // behind for the query:
 //
-//   cand = (p0, p1)   sorted positions of the nearest and second-nearest target point found,
-//   L                 a lower bound on the Euclidean distance from the query to EVERY OTHER target point.
+//   c0, c1   the nearest and second-nearest target point found (coordinates + original index, 16 B each,
+//            stored per query so that the next iteration's test is one coalesced streaming read),
+//   L        a lower bound on the Euclidean distance from the query to EVERY OTHER target point.
 //
 // ICP moves each query a little per iteration.  If the query has moved by `step` since the bound was
 // taken, every other point is still at least L - step away (triangle inequality), so whenever
-//       min(d(q, p0), d(q, p1))  <  L - step
+//       min(d(q, c0), d(q, c1))  <  L - step
 // the nearest neighbour is one of the two cached points and no search is needed (the idea of Greenspan &
 // Godin's cached-neighbour ICP, made exact in float arithmetic by the rounding margins below).  The
 // fused sweep (icp.cuh) runs that test for every query and sends only the failures here.
@@ -31,6 +32,14 @@ namespace b2 {
 
 constexpr float kRelUp = 1.000002f;    // > 1 + 16 ulp: turns a float distance into an upper bound
 constexpr float kRelDown = 0.999998f;  // < 1 - 16 ulp: turns a float distance into a lower bound
+
+// sqrt.approx.f32 (one MUFU, max relative error 2^-23): every use below is widened by kRelUp / kRelDown,
+// which is 16 ulp, so the IEEE-rounded (software-assisted) sqrt is not needed.
+__device__ __forceinline__ float sqrt_fast(float x) {
+  float y;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 struct Top3 {
   unsigned long long k0;  // best (d2, original index)
@@ -106,7 +115,7 @@ __device__ __forceinline__ CellBox cell_box(const GridView& g, float qx, float q
   thr = fminf(thr, bound2);
   CellBox b;
   if (thr < INFINITY) {
-    const float rs = __fadd_ru(__fadd_ru(__fmul_ru(__fsqrt_ru(thr), kRelUp), margin), g.slack);
+    const float rs = __fadd_ru(__fadd_ru(__fmul_ru(sqrt_fast(thr), kRelUp), margin), g.slack);
     b.xa = max(cell_coord(__fsub_rd(qx, rs), g.ox, g.inv_cell, g.nx), cx - max_span);
     b.xb = min(cell_coord(__fadd_ru(qx, rs), g.ox, g.inv_cell, g.nx), cx + max_span);
     b.ya = max(cell_coord(__fsub_rd(qy, rs), g.oy, g.inv_cell, g.ny), cy - max_span);
@@ -119,14 +128,6 @@ __device__ __forceinline__ CellBox cell_box(const GridView& g, float qx, float q
     b.za = max(cz - max_span, 0); b.zb = min(cz + max_span, g.nz - 1);
   }
   return b;
-}
-
-// Cost class of a box search (how many cells it will visit): queries of one class are searched by the
-// same warps, so that a warp's run time (its slowest lane) is close to its lanes' mean.
-constexpr int kCostClasses = 6;
-__device__ __forceinline__ int cost_class(const CellBox& b) {
-  const int cells = (b.xb - b.xa + 1) * (b.yb - b.ya + 1) * (b.zb - b.za + 1);
-  return cells <= 1 ? 0 : cells <= 2 ? 1 : cells <= 4 ? 2 : cells <= 8 ? 3 : cells <= 27 ? 4 : 5;
 }
 
 // Exact nearest / second nearest over the cells of `b`.  On return `lrest` is a lower bound on the
@@ -193,7 +194,7 @@ __device__ __forceinline__ void box_search(const GridView& g, float qx, float qy
 
 // lower bound on the distance to every target point other than top.p0 / top.p1
 __device__ __forceinline__ float top3_bound(const Top3& top, float lrest) {
-  const float l3 = top.b2 < INFINITY ? __fmul_rd(__fsqrt_rd(top.b2), kRelDown) : INFINITY;
+  const float l3 = top.b2 < INFINITY ? __fmul_rd(sqrt_fast(top.b2), kRelDown) : INFINITY;
   return fminf(l3, lrest);
 }
 

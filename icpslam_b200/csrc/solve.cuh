@@ -33,7 +33,7 @@ __device__ __forceinline__ bool jacobi_rotate(double& bp0, double& bp1, double& 
   const double al = bp0 * bp0 + bp1 * bp1 + bp2 * bp2;
   const double be = bq0 * bq0 + bq1 * bq1 + bq2 * bq2;
   const double ga = bp0 * bq0 + bp1 * bq1 + bp2 * bq2;
-  if (ga == 0.0 || ga * ga <= 1e-34 * (al * be)) return false;
+  if (ga == 0.0 || ga * ga <= 1e-30 * (al * be)) return false;  // |cos| <= 1e-15: below that a rotation is a no-op in fp64
   // t = tan(theta) = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)), zeta = (be - al) / (2 ga)
   //   = 2 ga * sign / (|be - al| + sqrt((be - al)^2 + 4 ga^2))            (one sqrt, one division)
   const double diff = be - al;

@@ -96,7 +96,7 @@ typedef struct b2icp_result {
 /* Device timings of the last b2icp_align / b2icp_align_batch chunk / b2icp_nn_search_device on this
  * handle (CUDA events on the handle's stream, recorded only when params.profile != 0). */
 typedef struct b2icp_timing {
-  int32_t nn_sweep_launches; /* launches of the fused sweep kernel that did work */
+  int32_t nn_sweep_launches; /* ICP iterations that did work (each = check + search + sums launches) */
   int32_t reserved;
   double nn_sweep_ms;        /* sum of their CUDA-event durations */
   double build_ms;           /* reserved */

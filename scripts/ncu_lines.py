@@ -56,5 +56,6 @@ def line(f, l):
         return src[f][l - 1].strip()[:100]
     except (KeyError, IndexError):
         return ""
-for k, (v, t, s) in sorted(agg.items(), key=lambda kv: -kv[1][2])[:topn]:
-    print(f"{s / max(tots,1):6.2%} smp {v / max(tot,1):6.2%} inst lanes={t / max(v, 1):5.1f}  {k[0]}:{k[1]}  {line(*k)}")
+key = (lambda kv: -kv[1][1]) if os.environ.get("BY") == "thr" else (lambda kv: -kv[1][2])
+for k, (v, t, s) in sorted(agg.items(), key=key)[:topn]:
+    print(f"{s / max(tots,1):6.2%} smp {v / max(tot,1):6.2%} inst {t/1e6:8.1f}M thr-inst lanes={t / max(v, 1):5.1f}  {k[0]}:{k[1]}  {line(*k)}")
