@@ -232,7 +232,6 @@ def main():
     ap.add_argument("--impl", default="b2icp", choices=["b2icp", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=4, help="sweeps timed on the CPU oracle (rank 0, N=1)")
     ap.add_argument("--grid-cell", type=float, default=0.0, help="neighbour-grid cell edge in metres (0 = auto); tuning only")
-    ap.add_argument("--presort", type=float, default=0.0, help="EXPERIMENT: pre-sort every sweep by cell of this edge (m)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b2icp" else args.warmup
 
@@ -268,12 +267,6 @@ def main():
     else:
         map_xyzw, sweeps = load_workload(rank * args.batch, args.batch)
 
-    if args.presort > 0:
-        o = map_xyzw[:, :3].min(axis=0)
-        def _sort(s):
-            c = np.floor((s[:, :3] - o) / args.presort).astype(np.int64)
-            return np.ascontiguousarray(s[np.lexsort((c[:, 0], c[:, 1], c[:, 2]))])
-        sweeps = [_sort(s) for s in sweeps]
     stream = torch.cuda.current_stream()
     reg = R.Registration(preset=R.PRESET_MAPPER, device=local_rank, profile=1, grid_cell=args.grid_cell)
     reg.setStream(stream.cuda_stream)
@@ -387,7 +380,7 @@ def main():
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("icp_sweep_p2p_dram_bytes_per_launch")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "icp_sweep_p2p", "peak_source": peak_src,
+                "traffic": traffic, "kernel": "icp_sweep_p2p (one launch = one ICP iteration of the whole batch)", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes / max(n_launch, 1),
                 "avg_launch_us": 1e6 * kernel_s / max(n_launch, 1), "launches": n_launch,
                 "nt_touched": nt_touched, "kernel_share_of_step": kernel_s / dev_s,

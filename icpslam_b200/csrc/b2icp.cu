@@ -29,6 +29,7 @@
 #include "gicp.cuh"
 #include "grid.cuh"
 #include "icp.cuh"
+#include "map.cuh"
 #include "nn.cuh"
 #include "solve.cuh"
 
@@ -118,6 +119,11 @@ struct b2icp_handle {
   std::vector<std::unique_ptr<ScanSlot>> slots;
   std::vector<std::unique_ptr<GridSlot>> grids;
   DeviceBuf states, tasks, unres_list, unres_count;
+  // K9: the mapper's point map (map.cuh)
+  DeviceBuf map_pts, map_keys, map_vals, map_slot_of, map_flags, map_tiles, map_stats;
+  size_t map_size = 0, map_table_cap = 0;
+  double map_resolution = 0.0;
+  bool map_grid_valid = false;
   DeviceBuf query, q_idx, q_d2, xf_in, xf_out, mat;
   IcpState* h_states = nullptr;  // pinned [kMaxBatch]: upload (init) and read-back
   ScanTask* h_tasks = nullptr;   // pinned [kMaxBatch]
@@ -467,6 +473,17 @@ int read_states(b2icp_handle* h, int B) {
       cudaEventElapsedTime(&ms, h->events[2 + 2 * it], h->events[3 + 2 * it]);
       t.nn_sweep_ms += ms;
     }
+    if (getenv("B2ICP_DUMP_ITERS")) {  // tuning only: per-iteration device time of the last batch
+      const int all = std::max(h->params.max_iterations, 1);
+      fprintf(stderr, "[b2icp] total %.1f us; per iteration (us):", 1e3 * t.total_ms);
+      for (int it = 0; it < all; ++it) {
+        cudaEventElapsedTime(&ms, h->events[2 + 2 * it], h->events[3 + 2 * it]);
+        int active = 0;
+        for (int i = 0; i < B; ++i) active += h->h_states[i].iter > it;
+        fprintf(stderr, " %d:%.1f(%d)", it, 1e3 * ms, active);
+      }
+      fprintf(stderr, "\n");
+    }
     t.nn_sweep_launches = ran;
     for (int i = 0; i < B; ++i) t.nn_searches += h->h_states[i].unresolved;
   }
@@ -509,8 +526,8 @@ double fitness_value(const IcpState& s) {
   return s.fitness_cnt > 0 ? s.fitness_sum / (double)s.fitness_cnt : DBL_MAX;
 }
 
-int nn_search_impl(b2icp_handle* h, const float4* d_q, size_t n, int* d_idx, float* d_d2) {
-  GridSlot& g = gslot(h, 0);
+int nn_search_impl(b2icp_handle* h, const float4* d_q, size_t n, int* d_idx, float* d_d2, int grid_index = 0) {
+  GridSlot& g = gslot(h, (size_t)grid_index);
   CK(h->unres_list.ensure(n * sizeof(int)));
   zero_counter<<<1, 1, 0, h->stream>>>(h->unres_count.as<unsigned int>());
   nn_search_kernel<<<(unsigned)((n + kSweepThreads - 1) / kSweepThreads), kSweepThreads, 0, h->stream>>>(
@@ -657,6 +674,13 @@ int b2icp_create(const b2icp_params* p, b2icp_handle** out) {
   std::memset(&h->timing, 0, sizeof(h->timing));
   derive_config(h);
   if (const char* e = getenv("B2ICP_QPT")) h->qpt_override = atoi(e);
+  if (const char* e = getenv("B2ICP_CARVEOUT")) {  // tuning only: shared-memory carve-out of the sweep, percent
+    const int pct = atoi(e);
+    cudaFuncSetAttribute(icp_sweep_p2p<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(icp_sweep_p2p<2>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(icp_sweep_p2p<4>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(icp_sweep_p2p<8>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  }
   slot(h, 0);
   gslot(h, 0);
   bool ok = cudaSetDevice(h->device) == cudaSuccess &&
@@ -682,6 +706,8 @@ int b2icp_destroy(b2icp_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto& s : h->slots) s->release();
   for (auto& g : h->grids) g->release();
+  for (DeviceBuf* b : {&h->map_pts, &h->map_keys, &h->map_vals, &h->map_slot_of, &h->map_flags, &h->map_tiles, &h->map_stats})
+    b->release();
   for (DeviceBuf* b : {&h->states, &h->tasks, &h->unres_list, &h->unres_count, &h->query, &h->q_idx, &h->q_d2, &h->xf_in,
                        &h->xf_out, &h->mat})
     b->release();
@@ -1021,6 +1047,204 @@ int b2icp_voxel_filter(b2icp_handle* h, const float* in_xyzw, size_t n, float le
   *n_out = (size_t)n_vox;
   g.valid = false;
   return B2ICP_OK;
+}
+
+// ---- K9: device-resident point map (map.cuh) ---------------------------------------------------------
+namespace {
+constexpr size_t kMapGrid = kMaxBatch + 4;  // grid slot that indexes the map for b2icp_map_nearest
+
+MapTable map_table(b2icp_handle* h) {
+  MapTable t;
+  t.keys = h->map_keys.as<unsigned long long>();
+  t.vals = h->map_vals.as<int>();
+  t.mask = (unsigned int)(h->map_table_cap - 1);
+  t.inv_res = 1.0 / h->map_resolution;
+  return t;
+}
+
+// table able to hold `want` voxels at load <= 0.5; growth re-enters the voxels of the current map
+int map_reserve(b2icp_handle* h, size_t want) {
+  size_t cap = std::max<size_t>(h->map_table_cap, 1024);
+  while (cap < 2 * want) cap *= 2;
+  if (cap == h->map_table_cap) return B2ICP_OK;
+  if (cap > (1ull << 31)) return fail(h, B2ICP_ERR_INVALID_ARG, "map too large");
+  h->map_keys.release();
+  h->map_vals.release();
+  CK(h->map_keys.ensure(cap * sizeof(unsigned long long)));
+  CK(h->map_vals.ensure(cap * sizeof(int)));
+  h->map_table_cap = cap;
+  CK(cudaMemsetAsync(h->map_keys.p, 0xFF, cap * sizeof(unsigned long long), h->stream));
+  CK(cudaMemsetAsync(h->map_vals.p, 0x7F, cap * sizeof(int), h->stream));
+  if (h->map_size) {
+    map_rehash<<<(unsigned)((h->map_size + 255) / 256), 256, 0, h->stream>>>(h->map_pts.as<float4>(), (int)h->map_size,
+                                                                         map_table(h));
+    h->launches += 1;
+  }
+  return B2ICP_OK;
+}
+
+// exclusive scan of flags[0..n) in place, flags[n] = total; returns the total through pinned memory
+int scan_flags(b2icp_handle* h, int* flags, size_t n, int* total) {
+  const int tiles = (int)((n + kScanTile - 1) / kScanTile);
+  CK(h->map_tiles.ensure((size_t)tiles * sizeof(int)));
+  CK(h->map_stats.ensure(sizeof(BBox)));
+  bbox_init<<<1, 32, 0, h->stream>>>(h->map_stats.as<BBox>());
+  scan_tile_sums<<<tiles, kScanThreads, 0, h->stream>>>(flags, (int)n, h->map_tiles.as<int>(), h->map_stats.as<BBox>());
+  scan_of_sums<<<1, kScanThreads, 0, h->stream>>>(h->map_tiles.as<int>(), tiles);
+  CK(cudaMemcpyAsync(&h->h_bbox[0], h->map_stats.p, sizeof(BBox), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  *total = h->h_bbox[0].occupied;  // flags are 0/1: non-zero entries = their sum
+  scan_apply<<<tiles, kScanThreads, 0, h->stream>>>(flags, (int)n, h->map_tiles.as<int>(), *total);
+  h->launches += 4;
+  return B2ICP_OK;
+}
+
+int map_insert_impl(b2icp_handle* h, const float* xyzw, size_t n, bool from_device, size_t* n_added) {
+  if (n_added) *n_added = 0;
+  if (!(h->map_resolution > 0)) return fail(h, B2ICP_ERR_INVALID_ARG, "b2icp_map_reset has not been called");
+  if (n == 0) return B2ICP_OK;
+  if (!xyzw) return fail(h, B2ICP_ERR_INVALID_ARG, "xyzw == NULL");
+  if (n > (size_t)INT32_MAX / 8 || h->map_size + n > (size_t)INT32_MAX / 8) return fail(h, B2ICP_ERR_INVALID_ARG, "map too large");
+  int rc = map_reserve(h, h->map_size + n);
+  if (rc) return rc;
+  if (h->map_pts.cap < (h->map_size + n) * sizeof(float4)) {  // grow, keeping the points
+    DeviceBuf bigger;
+    CK(bigger.ensure((h->map_size + n) * 2 * sizeof(float4)));
+    if (h->map_size) CK(cudaMemcpyAsync(bigger.p, h->map_pts.p, h->map_size * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->map_pts.release();
+    h->map_pts = bigger;
+    h->map_grid_valid = false;
+  }
+  const float4* pts = reinterpret_cast<const float4*>(xyzw);
+  if (!from_device) {
+    CK(h->xf_in.ensure(n * sizeof(float4)));
+    CK(cudaMemcpyAsync(h->xf_in.p, xyzw, n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+    pts = h->xf_in.as<float4>();
+  }
+  CK(h->map_slot_of.ensure(n * sizeof(int)));
+  CK(h->map_flags.ensure((n + 8) * sizeof(int)));
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  const MapTable t = map_table(h);
+  map_claim<<<blocks, 256, 0, h->stream>>>(pts, (int)n, t, h->map_slot_of.as<int>());
+  map_flag<<<blocks, 256, 0, h->stream>>>((int)n, t, h->map_slot_of.as<int>(), h->map_flags.as<int>());
+  int added = 0;
+  rc = scan_flags(h, h->map_flags.as<int>(), n, &added);
+  if (rc) return rc;
+  map_append<<<blocks, 256, 0, h->stream>>>(pts, (int)n, t, h->map_slot_of.as<int>(), h->map_flags.as<int>(),
+                                            h->map_pts.as<float4>(), (int)h->map_size);
+  h->launches += 3;
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  h->map_size += (size_t)added;
+  if (added) h->map_grid_valid = false;
+  if (n_added) *n_added = (size_t)added;
+  return B2ICP_OK;
+}
+
+int map_ensure_grid(b2icp_handle* h) {
+  if (h->map_size == 0) return fail(h, B2ICP_ERR_NO_TARGET, "the map is empty");
+  GridSlot& g = gslot(h, kMapGrid);
+  if (h->map_grid_valid && g.valid) return B2ICP_OK;
+  g.pts = h->map_pts.as<float4>();
+  GridSlot* gp = &g;
+  size_t n = h->map_size;
+  int rc = build_grids(h, &gp, &n, 1);
+  if (rc) return rc;
+  h->map_grid_valid = true;
+  return B2ICP_OK;
+}
+}  // namespace
+
+int b2icp_map_reset(b2icp_handle* h, double resolution) {
+  if (!h) return B2ICP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CK(cudaSetDevice(h->device));
+  if (!(resolution > 0) || !std::isfinite(resolution)) return fail(h, B2ICP_ERR_INVALID_ARG, "resolution must be > 0");
+  h->map_resolution = resolution;
+  h->map_size = 0;
+  h->map_grid_valid = false;
+  if (h->map_table_cap) {
+    CK(cudaMemsetAsync(h->map_keys.p, 0xFF, h->map_table_cap * sizeof(unsigned long long), h->stream));
+    CK(cudaMemsetAsync(h->map_vals.p, 0x7F, h->map_table_cap * sizeof(int), h->stream));
+  }
+  return B2ICP_OK;
+}
+
+int b2icp_map_insert(b2icp_handle* h, const float* xyzw, size_t n, size_t* n_added) {
+  if (!h) return B2ICP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CK(cudaSetDevice(h->device));
+  return map_insert_impl(h, xyzw, n, false, n_added);
+}
+
+int b2icp_map_insert_device(b2icp_handle* h, const float* d_xyzw, size_t n, size_t* n_added) {
+  if (!h) return B2ICP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CK(cudaSetDevice(h->device));
+  return map_insert_impl(h, d_xyzw, n, true, n_added);
+}
+
+int b2icp_map_size(b2icp_handle* h, size_t* n) {
+  if (!h || !n) return B2ICP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  *n = h->map_size;
+  return B2ICP_OK;
+}
+
+int b2icp_map_download(b2icp_handle* h, float* out_xyzw, size_t capacity, size_t* n) {
+  if (!h || !n) return B2ICP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CK(cudaSetDevice(h->device));
+  *n = h->map_size;
+  if (!out_xyzw || h->map_size == 0) return B2ICP_OK;
+  if (capacity < h->map_size) return fail(h, B2ICP_ERR_INVALID_ARG, "output buffer too small");
+  CK(cudaMemcpyAsync(out_xyzw, h->map_pts.p, h->map_size * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return B2ICP_OK;
+}
+
+int b2icp_map_nearest(b2icp_handle* h, const float* q_xyzw, size_t n, int32_t* idx, float* nn_xyzw, size_t* n_nn) {
+  if (!h) return B2ICP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CK(cudaSetDevice(h->device));
+  if (n_nn) *n_nn = 0;
+  if (n == 0) return B2ICP_OK;
+  if (!q_xyzw) return fail(h, B2ICP_ERR_INVALID_ARG, "q_xyzw == NULL");
+  int rc = map_ensure_grid(h);
+  if (rc) return rc;
+  CK(h->query.ensure(n * sizeof(float4)));
+  CK(h->q_idx.ensure((n + 8) * sizeof(int)));
+  CK(h->q_d2.ensure(n * sizeof(float)));
+  CK(cudaMemcpyAsync(h->query.p, q_xyzw, n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+  rc = nn_search_impl(h, h->query.as<float4>(), n, h->q_idx.as<int>(), h->q_d2.as<float>(), (int)kMapGrid);
+  if (rc) return rc;
+  if (idx) CK(cudaMemcpyAsync(idx, h->q_idx.p, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  if (nn_xyzw) {
+    CK(h->map_flags.ensure((n + 8) * sizeof(int)));
+    CK(h->xf_out.ensure(n * sizeof(float4)));
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    map_gather_flag<<<blocks, 256, 0, h->stream>>>(h->q_idx.as<int>(), (int)n, h->map_flags.as<int>());
+    int found = 0;
+    rc = scan_flags(h, h->map_flags.as<int>(), n, &found);
+    if (rc) return rc;
+    map_gather<<<blocks, 256, 0, h->stream>>>(h->q_idx.as<int>(), (int)n, h->map_flags.as<int>(), h->map_pts.as<float4>(),
+                                              h->xf_out.as<float4>());
+    h->launches += 2;
+    if (found) CK(cudaMemcpyAsync(nn_xyzw, h->xf_out.p, (size_t)found * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+    if (n_nn) *n_nn = (size_t)found;
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  return B2ICP_OK;
+}
+
+int b2icp_set_target_map(b2icp_handle* h) {
+  if (!h) return B2ICP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CK(cudaSetDevice(h->device));
+  if (h->map_size == 0) return fail(h, B2ICP_ERR_NO_TARGET, "the map is empty");
+  return set_target_impl(h, 0, h->map_pts.as<float>(), h->map_size, true);
 }
 
 int b2icp_get_timing(b2icp_handle* h, b2icp_timing* out) {

@@ -92,6 +92,8 @@ EXPORTS = [
     "b2icp_align", "b2icp_fitness", "b2icp_get_correspondences", "b2icp_nn_search", "b2icp_nn_search_device",
     "b2icp_transform_cloud", "b2icp_transform_cloud_f", "b2icp_align_batch", "b2icp_align_batch_device",
     "b2icp_set_stream", "b2icp_compute_covariances", "b2icp_voxel_filter", "b2icp_get_timing",
+    "b2icp_map_reset", "b2icp_map_insert", "b2icp_map_insert_device", "b2icp_map_size", "b2icp_map_download",
+    "b2icp_map_nearest", "b2icp_set_target_map",
     "b2icp_get_grid_info", "b2icp_host_alloc", "b2icp_host_free", "b2icp_last_error", "b2icp_status_string",
     "b2icp_version",
 ]
@@ -133,6 +135,14 @@ def load_library() -> C.CDLL:
     L.b2icp_set_stream.argtypes = [vp, vp]
     L.b2icp_compute_covariances.argtypes = [vp, vp, C.c_size_t, dp]
     L.b2icp_voxel_filter.argtypes = [vp, vp, C.c_size_t, C.c_float, vp, C.POINTER(C.c_size_t)]
+    szp = C.POINTER(C.c_size_t)
+    L.b2icp_map_reset.argtypes = [vp, C.c_double]
+    L.b2icp_map_insert.argtypes = [vp, vp, C.c_size_t, szp]
+    L.b2icp_map_insert_device.argtypes = [vp, vp, C.c_size_t, szp]
+    L.b2icp_map_size.argtypes = [vp, szp]
+    L.b2icp_map_download.argtypes = [vp, vp, C.c_size_t, szp]
+    L.b2icp_map_nearest.argtypes = [vp, vp, C.c_size_t, vp, vp, szp]
+    L.b2icp_set_target_map.argtypes = [vp]
     L.b2icp_get_timing.argtypes = [vp, C.POINTER(Timing)]
     L.b2icp_get_grid_info.argtypes = [vp, fp, ip, dp]
     L.b2icp_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
@@ -369,6 +379,44 @@ class Registration:
         n_out = C.c_size_t()
         self._check(self._L.b2icp_voxel_filter(self._h, _ptr(c), len(c), leaf, _ptr(out), C.byref(n_out)), "voxel_filter")
         return out[: n_out.value].copy()
+
+    # ---- OctreeMapper's point map (reference src/icpslam/octree_mapper.cpp:56-90), device-resident
+    def resetMap(self, resolution: float):
+        """OctreeMapper::resetMap."""
+        self._check(self._L.b2icp_map_reset(self._h, float(resolution)), "map_reset")
+
+    def addPointsToMap(self, cloud) -> int:
+        """OctreeMapper::addPointsToMap: one point per voxel, first come wins; returns the points added."""
+        c = _cloud(cloud)
+        n_added = C.c_size_t()
+        self._check(self._L.b2icp_map_insert(self._h, _ptr(c), len(c), C.byref(n_added)), "map_insert")
+        return n_added.value
+
+    def mapSize(self) -> int:
+        n = C.c_size_t()
+        self._check(self._L.b2icp_map_size(self._h, C.byref(n)), "map_size")
+        return n.value
+
+    def mapCloud(self) -> np.ndarray:
+        n = self.mapSize()
+        out = np.empty((n, 4), np.float32)
+        got = C.c_size_t()
+        self._check(self._L.b2icp_map_download(self._h, _ptr(out) if n else None, n, C.byref(got)), "map_download")
+        return out[: got.value]
+
+    def approxNearestNeighbors(self, cloud):
+        """OctreeMapper::approxNearestNeighbors with the exact nearest neighbour: (indices into the map,
+        nn_cloud = the map point of every query that has one, in query order)."""
+        c = _cloud(cloud)
+        idx = np.empty(len(c), np.int32)
+        nn = np.empty((len(c), 4), np.float32)
+        n_nn = C.c_size_t()
+        self._check(self._L.b2icp_map_nearest(self._h, _ptr(c), len(c), _ptr(idx), _ptr(nn), C.byref(n_nn)), "map_nearest")
+        return idx, nn[: n_nn.value].copy()
+
+    def setInputTargetFromMap(self):
+        """The map becomes the registration target without leaving the device."""
+        self._check(self._L.b2icp_set_target_map(self._h), "set_target_map")
 
     def setStream(self, cuda_stream: int):
         self._check(self._L.b2icp_set_stream(self._h, C.c_void_p(cuda_stream)), "set_stream")

@@ -195,6 +195,28 @@ int b2icp_compute_covariances(b2icp_handle* h, const float* xyzw, size_t n, doub
 int b2icp_voxel_filter(b2icp_handle* h, const float* in_xyzw, size_t n, float leaf, float* out_xyzw,
                        size_t* n_out);
 
+/* ---- the mapper's point map (OctreeMapper::map_octree_ / map_cloud_, octree_mapper.h:82-83) --------------
+ * b2icp_map_reset          OctreeMapper::resetMap (octree_mapper.cpp:56-60): empty map at `resolution`.
+ * b2icp_map_insert         OctreeMapper::addPointsToMap (octree_mapper.cpp:63-71): a point enters the map iff
+ *                          no earlier point (of the map or of this call, in input order) lies in its voxel;
+ *                          new points are appended in input order.  *n_added (nullable) = points added.
+ *                          A voxel is a cell of the lattice floor(p / resolution) (see csrc/map.cuh).
+ * b2icp_map_nearest        OctreeMapper::approxNearestNeighbors (octree_mapper.cpp:73-90) with the engine's
+ *                          EXACT nearest neighbour instead of PCL's greedy octree descent: idx[i] (nullable) =
+ *                          index in the map of the point nearest to query i, -1 if the query is not finite;
+ *                          nn_xyzw (nullable, room for n points) = those map points compacted in query order
+ *                          (the reference's nn_cloud, duplicates included), *n_nn their number.
+ * b2icp_set_target_map     the map itself becomes the registration target (device to device): scan-to-map
+ *                          localisation without the gather (BASELINE configs[1] and [4]).
+ * The map lives in device memory; download / size are for the caller's bookkeeping and publishing. */
+int b2icp_map_reset(b2icp_handle* h, double resolution);
+int b2icp_map_insert(b2icp_handle* h, const float* xyzw, size_t n, size_t* n_added);
+int b2icp_map_insert_device(b2icp_handle* h, const float* d_xyzw, size_t n, size_t* n_added);
+int b2icp_map_size(b2icp_handle* h, size_t* n);
+int b2icp_map_download(b2icp_handle* h, float* out_xyzw, size_t capacity, size_t* n);
+int b2icp_map_nearest(b2icp_handle* h, const float* q_xyzw, size_t n, int32_t* idx, float* nn_xyzw, size_t* n_nn);
+int b2icp_set_target_map(b2icp_handle* h);
+
 int b2icp_get_timing(b2icp_handle* h, b2icp_timing* out);
 /* Neighbour grid of the current target (the structure that replaces the FLANN k-d tree): cell edge,
  * dims3 = {nx, ny, nz}, mean points per occupied cell.  Any pointer may be NULL. */

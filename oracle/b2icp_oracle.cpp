@@ -28,6 +28,7 @@
 #include <cstring>
 #include <limits>
 #include <numeric>
+#include <unordered_set>
 #include <vector>
 
 #ifdef _OPENMP
@@ -671,6 +672,45 @@ int b2o_fitness(const float* src, size_t ns, const float* tgt, size_t nt, const 
       ++nr;
     }
   *out = nr > 0 ? sum / (double)nr : std::numeric_limits<double>::max();
+  return B2ICP_OK;
+}
+
+/* OctreeMapper::addPointsToMap (reference src/icpslam/octree_mapper.cpp:63-71): for each
+ * point in order, `if (!isVoxelOccupiedAtPoint(p)) addPointToCloud(p)`.  Voxels are the cells of the global
+ * lattice floor(p / resolution) (PCL's lattice is anchored on the octree's bounding box, which depends on the
+ * insertion history: documented deviation).  Non-finite points are skipped. */
+int b2o_map_insert(const float* map, size_t n_map, const float* in, size_t n, double resolution, float* out_added,
+                   size_t* n_added) {
+  if (!n_added) return B2ICP_ERR_INVALID_ARG;
+  *n_added = 0;
+  if (!(resolution > 0)) return B2ICP_ERR_INVALID_ARG;
+  if (n == 0) return B2ICP_OK;
+  if (!in || !out_added || (n_map && !map)) return B2ICP_ERR_INVALID_ARG;
+  const double inv = 1.0 / resolution;
+  auto key_of = [&](const float* p, uint64_t& key) {
+    if (!(std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2]))) return false;
+    const int64_t ix = (int64_t)std::floor((double)p[0] * inv), iy = (int64_t)std::floor((double)p[1] * inv),
+                  iz = (int64_t)std::floor((double)p[2] * inv);
+    key = ((uint64_t)(ix & 0x1FFFFF) << 42) | ((uint64_t)(iy & 0x1FFFFF) << 21) | (uint64_t)(iz & 0x1FFFFF);
+    return true;
+  };
+  std::unordered_set<uint64_t> occupied;
+  occupied.reserve((n_map + n) * 2);
+  uint64_t key;
+  for (size_t i = 0; i < n_map; ++i)
+    if (key_of(map + 4 * i, key)) occupied.insert(key);
+  size_t m = 0;
+  for (size_t i = 0; i < n; ++i) {
+    if (!key_of(in + 4 * i, key)) continue;
+    if (occupied.insert(key).second) {
+      out_added[4 * m] = in[4 * i];
+      out_added[4 * m + 1] = in[4 * i + 1];
+      out_added[4 * m + 2] = in[4 * i + 2];
+      out_added[4 * m + 3] = 1.0f;
+      ++m;
+    }
+  }
+  *n_added = m;
   return B2ICP_OK;
 }
 

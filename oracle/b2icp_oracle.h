@@ -75,6 +75,11 @@ int b2o_fitness(const float* src_xyzw, size_t n_src, const float* tgt_xyzw, size
 
 /* pcl::VoxelGrid with a cubic leaf (Appendix A.8; reference icp_odometer.cpp:96-101). out holds n points. */
 int b2o_voxel_filter(const float* in_xyzw, size_t n, float leaf, float* out_xyzw, size_t* n_out);
+/* OctreeMapper::addPointsToMap (reference src/icpslam/octree_mapper.cpp:63-71) on the global voxel lattice
+ * floor(p / resolution): the points of `in` that enter a map already holding `map` (first come wins, input
+ * order), written to out_added (room for n points). */
+int b2o_map_insert(const float* map_xyzw, size_t n_map, const float* in_xyzw, size_t n, double resolution,
+                   float* out_added, size_t* n_added);
 
 /* Pose6DOF algebra (reference src/utils/pose6DOF.cpp:98-105 compose, :117-122 inverse,
  * :185-190 fromEigenMatrix).  pose7 = {px,py,pz,qw,qx,qy,qz}. */

@@ -267,6 +267,21 @@ def voxel_filter(cloud, leaf: float) -> np.ndarray:
     return out[: n_out.value].copy()
 
 
+def map_insert(map_cloud, cloud, resolution: float) -> np.ndarray:
+    """Points of `cloud` that OctreeMapper::addPointsToMap appends to a map holding `map_cloud`."""
+    cloud = _cloud(cloud)
+    m = _cloud(map_cloud) if map_cloud is not None and len(map_cloud) else np.zeros((0, 4), np.float32)
+    out = np.empty_like(cloud)
+    n_out = C.c_size_t()
+    L = lib()
+    fp = C.POINTER(C.c_float)
+    L.b2o_map_insert.argtypes = [fp, C.c_size_t, fp, C.c_size_t, C.c_double, fp, C.POINTER(C.c_size_t)]
+    rc = L.b2o_map_insert(_f(m) if len(m) else None, len(m), _f(cloud), len(cloud), resolution, _f(out), C.byref(n_out))
+    if rc != 0:
+        raise RuntimeError(f"b2o_map_insert rc={rc}")
+    return out[: n_out.value].copy()
+
+
 def pose_compose(a, b):
     a = np.ascontiguousarray(a, np.float64)
     b = np.ascontiguousarray(b, np.float64)

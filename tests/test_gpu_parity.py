@@ -324,3 +324,70 @@ def test_voxel_filter_edge_cases(R, oracle):
     assert np.array_equal(out, wide)
     _, _, sc = synth.planar_stream(3, 1)
     assert np.array_equal(reg.voxelFilterCloud(sc[0], 0.1), oracle.voxel_filter(sc[0], 0.1))
+
+
+# ------------------------------------------------------------------------------------------------
+# K9: the mapper's point map (reference src/icpslam/octree_mapper.cpp:56-90)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_map_insert_bit_exact_and_in_scan_order(R, oracle):
+    _, _, sw = synth.sweep_sequence(9, 4, n_beams=64, n_az=256)
+    reg = R.Registration(preset=R.PRESET_MAPPER)
+    reg.resetMap(0.2)
+    ref = np.zeros((0, 4), np.float32)
+    for s in sw:
+        added = oracle.map_insert(ref, s, 0.2)
+        n = reg.addPointsToMap(s)
+        assert n == len(added)
+        ref = np.concatenate([ref, added])
+        assert reg.mapSize() == len(ref)
+    assert np.array_equal(reg.mapCloud(), ref)          # same points, same (scan) order
+    assert reg.addPointsToMap(sw[0]) == 0               # every voxel of sweep 0 is taken
+    reg.resetMap(0.5)                                   # resetMap: new resolution, empty map, table reused
+    assert reg.mapSize() == 0
+    assert reg.addPointsToMap(sw[1]) == len(oracle.map_insert(None, sw[1], 0.5))
+
+
+@pytest.mark.gpu
+def test_map_insert_edge_cases(R, oracle):
+    reg = R.Registration(preset=R.PRESET_MAPPER)
+    with pytest.raises(R.B2icpError):
+        reg.addPointsToMap(np.zeros((4, 4), np.float32))          # no resetMap yet
+    reg.resetMap(0.2)
+    assert reg.addPointsToMap(np.zeros((0, 4), np.float32)) == 0
+    dup = np.tile(np.array([[1.0, 2.0, 3.0, 1.0]], np.float32), (1000, 1))
+    assert reg.addPointsToMap(dup) == 1                           # collisions: one voxel, first point wins
+    bad = np.array([[np.nan, 0, 0, 1], [0.01, 0.01, 0.01, 1], [np.inf, 1, 1, 1], [-0.01, 0.01, 0.01, 1]], np.float32)
+    assert reg.addPointsToMap(bad) == 2                           # non-finite points are skipped
+    m = reg.mapCloud()
+    assert np.array_equal(m[1:], bad[[1, 3]]) and np.array_equal(m[0], dup[0])
+    # growth across table resizes keeps every earlier voxel occupied
+    rng = np.random.default_rng(5)
+    big = np.concatenate([rng.uniform(-50, 50, (200_000, 3)).astype(np.float32), np.ones((200_000, 1), np.float32)], axis=1)
+    ref = oracle.map_insert(m, big, 0.2)
+    assert reg.addPointsToMap(big) == len(ref)
+    assert np.array_equal(reg.mapCloud()[3:], ref)
+
+
+@pytest.mark.gpu
+def test_map_nearest_matches_oracle_and_feeds_icp(R, oracle):
+    _, _, sw = synth.sweep_sequence(10, 3, n_beams=64, n_az=256)
+    reg = R.Registration(preset=R.PRESET_MAPPER)
+    reg.resetMap(0.2)
+    reg.addPointsToMap(sw[0])
+    reg.addPointsToMap(sw[1])
+    m = reg.mapCloud()
+    idx, nn = reg.approxNearestNeighbors(sw[2])
+    oi, _ = oracle.nn_brute(m, sw[2])
+    assert np.array_equal(idx, oi)
+    assert np.array_equal(nn, m[oi])                    # nn_cloud: map points in query order, duplicates kept
+    # the map as the target, device to device: same registration as uploading the downloaded map
+    reg.setInputTargetFromMap()
+    reg.setInputSource(sw[2])
+    reg.align()
+    T_map = reg.getFinalTransformation()
+    reg2 = R.Registration(preset=R.PRESET_MAPPER)
+    reg2.setInputTarget(m)
+    reg2.setInputSource(sw[2])
+    reg2.align()
+    assert np.array_equal(T_map, reg2.getFinalTransformation())
