@@ -291,39 +291,28 @@ class OctreeMapper {
   void advertisePublishers() {}
   void registerSubscribers() {}
 
-  // octree_mapper.cpp:56-60
+  // octree_mapper.cpp:56-60.  The map lives in device memory behind the C ABI (b2icp_map_*, csrc/map.cuh).
   void resetMap() {
+    last_status = b2icp_map_reset(search_.get(), prm_.octree_resolution);
     map_cloud_.reset(new Cloud());
-    occupied_.clear();
-    map_dirty_ = true;
+    map_cloud_stale_ = false;
   }
   // octree_mapper.cpp:63-71: at most one point per octree_resolution voxel, first come wins, scan order kept
   void addPointsToMap(const Cloud::Ptr& input_cloud) {
-    const double inv = 1.0 / prm_.octree_resolution;
-    for (const PointXYZ& p : input_cloud->points) {
-      const int64_t ix = (int64_t)std::floor(p.x * inv), iy = (int64_t)std::floor(p.y * inv), iz = (int64_t)std::floor(p.z * inv);
-      const uint64_t key = ((uint64_t)(ix & 0x1FFFFF) << 42) | ((uint64_t)(iy & 0x1FFFFF) << 21) | (uint64_t)(iz & 0x1FFFFF);
-      if (occupied_.insert(key).second) {
-        map_cloud_->points.push_back(PointXYZ{p.x, p.y, p.z, 1.0f});
-        map_dirty_ = true;
-      }
-    }
+    size_t added = 0;
+    last_status = b2icp_map_insert(search_.get(), input_cloud->data(), input_cloud->size(), &added);
+    if (added) map_cloud_stale_ = true;
   }
   // octree_mapper.cpp:73-90 with the engine's exact nearest neighbour (see the header comment)
   bool approxNearestNeighbors(const Cloud::Ptr& cloud, Cloud::Ptr& nearest_neighbors) {
     nearest_neighbors->points.clear();
-    if (map_cloud_->points.empty() || cloud->points.empty()) return false;
-    if (map_dirty_) {
-      last_status = b2icp_set_target(search_.get(), map_cloud_->data(), map_cloud_->size());
-      if (last_status) return false;
-      map_dirty_ = false;
-    }
-    std::vector<int32_t> idx(cloud->size());
-    last_status = b2icp_nn_search(search_.get(), cloud->data(), cloud->size(), idx.data(), nullptr);
-    if (last_status) return false;
-    for (int32_t i : idx)
-      if (i >= 0) nearest_neighbors->points.push_back(map_cloud_->points[(size_t)i]);
-    return !nearest_neighbors->points.empty();
+    if (mapSize() == 0 || cloud->points.empty()) return false;
+    nearest_neighbors->points.resize(cloud->size());
+    size_t n_nn = 0;
+    last_status = b2icp_map_nearest(search_.get(), cloud->data(), cloud->size(), nullptr, nearest_neighbors->data(), &n_nn);
+    if (last_status) n_nn = 0;
+    nearest_neighbors->points.resize(n_nn);
+    return n_nn > 0;
   }
   // octree_mapper.cpp:92-99: pcl_ros::transformPointCloud(tf::Transform) == float 4x4
   void transformCloudToPoseFrame(const Cloud::Ptr& in_cloud, const Pose6DOF& pose, Cloud::Ptr& out_cloud) {
@@ -352,7 +341,7 @@ class OctreeMapper {
   bool refineTransformAndGrowMap(double stamp, const Cloud::Ptr& cloud, const Pose6DOF& raw_pose, Pose6DOF& transform) {
     Cloud::Ptr cloud_in_map(new Cloud());
     transformCloudToPoseFrame(cloud, raw_pose, cloud_in_map);
-    if (map_cloud_->points.empty()) {
+    if (mapSize() == 0) {
       addPointsToMap(cloud_in_map);
       return false;
     }
@@ -367,7 +356,21 @@ class OctreeMapper {
     }
     return false;
   }
-  const Cloud::Ptr& mapCloud() const { return map_cloud_; }
+  size_t mapSize() {
+    size_t n = 0;
+    b2icp_map_size(search_.get(), &n);
+    return n;
+  }
+  // host copy of map_cloud_ (what the reference publishes, octree_mapper.cpp:45-49): fetched on demand
+  const Cloud::Ptr& mapCloud() {
+    if (map_cloud_stale_) {
+      size_t n = mapSize();
+      map_cloud_->points.resize(n);
+      last_status = b2icp_map_download(search_.get(), map_cloud_->data(), n, &n);
+      map_cloud_stale_ = false;
+    }
+    return map_cloud_;
+  }
 
   int last_status = 0;
   b2icp_result last_result{};
@@ -376,8 +379,7 @@ class OctreeMapper {
   OctreeMapperParams prm_;
   Engine icp_, search_;
   Cloud::Ptr map_cloud_;
-  std::unordered_set<uint64_t> occupied_;
-  bool map_dirty_ = true;
+  bool map_cloud_stale_ = false;
 };
 
 }  // namespace b2

@@ -165,6 +165,107 @@ def test_config4_unit_64k_scan_pair_30_iterations(R, oracle):
     assert np.array_equal(idx, o["corr_idx"])
 
 
+def test_config2_sweep_vs_accumulated_map_through_the_device_map(R, oracle):
+    """BASELINE.json configs[1] at reduced map size, end to end on the device: the map is grown by
+    addPointsToMap from 12 sweeps in the map frame (one point per 0.2 m voxel), becomes the target without
+    leaving the GPU, and the next sweep is registered with 30 iterations; the oracle does the same steps
+    (map_insert restatement, then align) on the host."""
+    _, poses, sw = synth.sweep_sequence(2, 14, n_az=256)
+    reg = R.Registration(preset=R.PRESET_MAPPER)
+    reg.resetMap(0.2)
+    ref = np.zeros((0, 4), np.float32)
+    for k in range(12):
+        T = poses[k]
+        w = synth.as_xyzw(sw[k][:, :3].astype(np.float64) @ T[:3, :3].T + T[:3, 3])
+        reg.addPointsToMap(w)
+        ref = np.concatenate([ref, oracle.map_insert(ref, w, 0.2)])
+    assert reg.mapSize() == len(ref) and len(ref) > 50_000
+    # the next sweep, placed with its predecessor's pose (the odometry guess of icpslam.cpp:135)
+    T = poses[11]
+    q = synth.as_xyzw(sw[12][:, :3].astype(np.float64) @ T[:3, :3].T + T[:3, 3])
+    reg.setInputTargetFromMap()
+    reg.setInputSource(q)
+    reg.align()
+    o = oracle.align(oracle.default_params("mapper"), q, ref, record_iter=-1)
+    assert reg.iterations == o["iterations"]
+    assert_transform_close(reg.getFinalTransformation(), o["T"])
+    idx, _ = reg.getCorrespondences()
+    assert np.array_equal(idx, o["corr_idx"])
+
+
+def test_config5_localisation_voxel_downsample_50_iterations(R, oracle):
+    """BASELINE.json configs[4] at reduced map size: raw sweep -> voxel filter (leaf 0.2) -> 50 ICP iterations
+    against a fixed global map; every stage against the oracle."""
+    _, poses, sw = synth.sweep_sequence(5, 8, n_az=512)
+    reg = R.Registration(preset=R.PRESET_MAPPER, max_iterations=50)
+    reg.resetMap(0.2)
+    for k in range(7):
+        T = poses[k]
+        reg.addPointsToMap(synth.as_xyzw(sw[k][:, :3].astype(np.float64) @ T[:3, :3].T + T[:3, 3]))
+    gmap = reg.mapCloud()
+    T = poses[6]
+    raw = synth.as_xyzw(sw[7][:, :3].astype(np.float64) @ T[:3, :3].T + T[:3, 3])
+    q = reg.voxelFilterCloud(raw, 0.2)
+    assert np.array_equal(q, oracle.voxel_filter(raw, 0.2))
+    reg.setInputTargetFromMap()
+    reg.setInputSource(q)
+    reg.align()
+    p = oracle.default_params("mapper")
+    p.max_iterations = 50
+    o = oracle.align(p, q, gmap, record_iter=-1)
+    assert reg.iterations == o["iterations"]
+    assert_transform_close(reg.getFinalTransformation(), o["T"])
+    idx, _ = reg.getCorrespondences()
+    assert np.array_equal(idx, o["corr_idx"])
+
+
+def test_config5_full_size_5m_point_map_properties(R):
+    """BASELINE.json configs[4] at FULL map size (5 M points, 64k-point query), through size-independent
+    properties: every query's reported neighbour is at the reported distance, no sampled map point is closer
+    (exactness on a random subset), and ICP against the big map undoes a known small rigid motion."""
+    rng = np.random.default_rng(505)
+    n_map, n_q = 5_000_000, 65_536
+    # a 600 m x 400 m terrain: gentle hills + walls, about 20 points / m^2
+    xy = rng.uniform([-300, -200], [300, 200], (n_map, 2))
+    z = 2.0 * np.sin(xy[:, 0] / 30.0) * np.cos(xy[:, 1] / 40.0) + rng.normal(0, 0.02, n_map)
+    wall = rng.random(n_map) < 0.15
+    z[wall] = rng.uniform(0, 6, wall.sum())
+    xy[wall, 0] = np.round(xy[wall, 0] / 25.0) * 25.0 + rng.normal(0, 0.02, wall.sum())
+    gmap = np.concatenate([xy, z[:, None], np.ones((n_map, 1))], axis=1).astype(np.float32)
+    sel = np.where((np.abs(gmap[:, 0] - 40) < 45) & (np.abs(gmap[:, 1] + 20) < 45))[0]
+    src_idx = rng.choice(sel, n_q, replace=False)
+    ang = np.radians(0.4)
+    Tt = np.eye(4)
+    Tt[:3, :3] = [[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]]
+    Tt[:3, 3] = [0.12, -0.07, 0.03]
+    c = gmap[src_idx, :3].astype(np.float64).mean(axis=0)
+    # q = T^-1 applied about the patch centre, plus sensor noise: ICP must find ~T
+    Ti = np.linalg.inv(Tt)
+    q = (gmap[src_idx, :3].astype(np.float64) - c) @ Ti[:3, :3].T + Ti[:3, 3] + c + rng.normal(0, 0.01, (n_q, 3))
+    q = synth.as_xyzw(q)
+    reg = R.Registration(preset=R.PRESET_MAPPER, max_iterations=50)
+    reg.setInputTarget(gmap)
+    idx, d2 = reg.nearestKSearch1(q)
+    assert idx.min() >= 0 and idx.max() < n_map
+    d = ((q[:, :3].astype(np.float32) - gmap[idx, :3]) ** 2)
+    assert np.allclose(d2, d[:, 0] + d[:, 1] + d[:, 2], rtol=1e-5, atol=1e-9)
+    probe = rng.choice(n_q, 256, replace=False)                     # exhaustive check of a subset
+    for i in probe[:64]:
+        dd = ((gmap[:, :3] - q[i, :3]) ** 2).astype(np.float32)
+        full = dd[:, 0] + dd[:, 1] + dd[:, 2]
+        assert full.min() >= d2[i] * (1 - 1e-6) and full[idx[i]] <= full.min() * (1 + 1e-6)
+    reg.setInputSource(q)
+    reg.align()
+    T = reg.getFinalTransformation()
+    # expected transform maps q back onto the map: x -> R (x - c) + t + c
+    Texp = np.eye(4)
+    Texp[:3, :3] = Tt[:3, :3]
+    Texp[:3, 3] = Tt[:3, 3] + c - Tt[:3, :3] @ c
+    assert np.abs(T[:3, :3] - Texp[:3, :3]).max() < 2e-4
+    assert np.abs(T[:3, 3] - Texp[:3, 3]).max() < 5e-3
+    assert reg.iterations <= 50 and reg.hasConverged()
+
+
 def test_config3_planar_1080pt_scan_to_scan(R, oracle):
     """BASELINE.json configs[2]: 2-D planar 1080-pt scans (z = 0: rank-2 covariance, nz = 1 grid)."""
     _, _, scans = synth.planar_stream(3, 6)
