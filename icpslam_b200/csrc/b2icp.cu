@@ -44,6 +44,7 @@ constexpr int kUnboundedRings = 3;        // ring budget of unbounded searches b
 constexpr double kTargetOccupancy = 2.5;  // points per occupied cell the auto-sizing aims at
 constexpr double kMaxOccupancy = 4.0;     // above this the grid is rebuilt with smaller cells
 constexpr float kCacheMarginFrac = 0.05f;  // nncache.cuh: box-search margin as a fraction of the cell edge
+constexpr int kFirstSweepQpt = 2;         // slab length (x 32 queries per warp) of the first sweep of a batch
 constexpr int kMaxBatch = 64;             // scans advanced together by one sweep launch
 
 struct DeviceBuf {
@@ -135,6 +136,7 @@ struct b2icp_handle {
   b2icp_timing timing;
   long long launches = 0;
   int qpt_override = 0;  // B2ICP_QPT environment variable (tuning only)
+  std::vector<int> qpt_sched;  // B2ICP_QPT_SCHED="2,4,8": slab length per iteration, last value repeats (tuning only)
   double* h_gicp_partials = nullptr;  // pinned read-back of gicp_fdf_kernel's per-CTA sums
   size_t h_gicp_partials_cap = 0;
   long gicp_evals = 0;
@@ -433,14 +435,23 @@ int run_batch(b2icp_handle* h, int B, const float* guesses) {
   const long long want = 2LL * 148 * kSweepMinCtas;
   const int qpt = h->qpt_override > 0 ? h->qpt_override
                                       : (ctas_at(8) >= want ? 8 : (ctas_at(4) >= want ? 4 : (ctas_at(2) >= want ? 2 : 1)));
-  dim3 grid((unsigned)((max_n + (size_t)kSweepThreads * qpt - 1) / ((size_t)kSweepThreads * qpt)), (unsigned)B, 1);
+  // The slab length can change from one launch to the next (the work list lives inside a launch).  The first
+  // sweeps search most queries, so their warps are long-running whatever the slab: shorter slabs there keep
+  // the last wave of CTAs from running on a third of the machine.
+  auto qpt_at = [&](int it) {
+    if (!h->qpt_sched.empty()) return h->qpt_sched[std::min<size_t>((size_t)it, h->qpt_sched.size() - 1)];
+    // measured on B200 (32 x 64k sweeps, scans/s): 8 everywhere 10 144; 2,8.. 10 451; 2,4,4,8.. 10 533; 2,4,4,4,4,8.. 10 571
+    return it == 0 ? std::min(qpt, kFirstSweepQpt) : (it <= 4 ? std::min(qpt, 4) : qpt);
+  };
   for (int it = 0; it < iters; ++it) {
     if (prof) CK(cudaEventRecord(h->events[2 + 2 * it], h->stream));
-    if (qpt == 8)
+    const int q = qpt_at(it);
+    const dim3 grid((unsigned)((max_n + (size_t)kSweepThreads * q - 1) / ((size_t)kSweepThreads * q)), (unsigned)B, 1);
+    if (q == 8)
       icp_sweep_p2p<8><<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>(), h->cfg);
-    else if (qpt == 4)
+    else if (q == 4)
       icp_sweep_p2p<4><<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>(), h->cfg);
-    else if (qpt == 2)
+    else if (q == 2)
       icp_sweep_p2p<2><<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>(), h->cfg);
     else
       icp_sweep_p2p<1><<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>(), h->cfg);
@@ -674,6 +685,13 @@ int b2icp_create(const b2icp_params* p, b2icp_handle** out) {
   std::memset(&h->timing, 0, sizeof(h->timing));
   derive_config(h);
   if (const char* e = getenv("B2ICP_QPT")) h->qpt_override = atoi(e);
+  if (const char* e = getenv("B2ICP_QPT_SCHED"))
+    for (const char* p = e; *p;) {
+      const int v = atoi(p);
+      h->qpt_sched.push_back(v >= 8 ? 8 : (v >= 4 ? 4 : (v >= 2 ? 2 : 1)));
+      while (*p && *p != ',') ++p;
+      if (*p == ',') ++p;
+    }
   if (const char* e = getenv("B2ICP_CARVEOUT")) {  // tuning only: shared-memory carve-out of the sweep, percent
     const int pct = atoi(e);
     cudaFuncSetAttribute(icp_sweep_p2p<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
