@@ -266,6 +266,29 @@ def test_config5_full_size_5m_point_map_properties(R):
     assert reg.iterations <= 50 and reg.hasConverged()
 
 
+def test_cached_neighbour_certificate_never_changes_a_correspondence(R, oracle):
+    """The sweep skips the search of a query whenever its cached-neighbour certificate holds (csrc/nncache.cuh).
+    The result must stay the exact nearest neighbour: compare EVERY iteration's correspondences with the oracle
+    (max_iterations = k stops both after k sweeps) on tie-free real data, on a tie-heavy integer lattice, on a
+    target with duplicated points (the mapper's NN cloud), with a tight and a wide gate."""
+    _, _, sw = synth.sweep_sequence(6, 2, n_beams=64, n_az=256)
+    lat_t = synth.integer_cloud(11, 6000, -12, 12)
+    lat_s = synth.as_xyzw(synth.integer_cloud(12, 4000, -12, 12, unique=False)[:, :3] * 1.0 + np.float32(0.25))
+    dup_t = np.concatenate([sw[0], sw[0][::3], sw[0][::7]])
+    cases = [(sw[1], sw[0], 1.0), (sw[1], sw[0], 0.3), (sw[1], sw[0], 25.0), (lat_s, lat_t, 1.5), (sw[1], dup_t, 1.0)]
+    for src, tgt, gate in cases:
+        for k in (1, 2, 3, 5, 8, 13, 30):
+            reg, _, o = run_pair(R, oracle, src, tgt, R.PRESET_MAPPER, max_iterations=k, max_correspondence_distance=gate)
+            idx, d2 = reg.getCorrespondences()
+            assert reg.iterations == o["iterations"], (gate, k)
+            assert np.array_equal(idx, o["corr_idx"]), (gate, k, int((idx != o["corr_idx"]).sum()))
+            keep = idx >= 0
+            assert np.array_equal(d2[keep], o["corr_d2"][keep])
+            assert_transform_close(reg.getFinalTransformation(), o["T"])
+            if reg.iterations < k:
+                break
+
+
 def test_config3_planar_1080pt_scan_to_scan(R, oracle):
     """BASELINE.json configs[2]: 2-D planar 1080-pt scans (z = 0: rank-2 covariance, nz = 1 grid)."""
     _, _, scans = synth.planar_stream(3, 6)
