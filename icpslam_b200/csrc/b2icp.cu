@@ -403,7 +403,7 @@ int run_batch(b2icp_handle* h, int B, const float* guesses) {
     t.partials = s.partials.as<double>();
     t.state = h->states.as<IcpState>() + i;
     t.n = (int)s.src.n;
-    t.pad = 0;
+    t.pad = 1;  // the loop leaves a certificate per query: getFitnessScore starts from it
     IcpState& st = h->h_states[i];
     std::memset(&st, 0, sizeof(st));
     for (int k = 0; k < 16; ++k) {
@@ -552,13 +552,70 @@ int nn_search_impl(b2icp_handle* h, const float4* d_q, size_t n, int* d_idx, flo
 
 #include "gicp_host.inl"
 
+// GICP over a batch: the scans run one after the other through slot 0 (the BFGS recursion is driven from the
+// host, gicp_host.inl), with the same target conventions as the point-to-point batch.
+int gicp_batch_impl(b2icp_handle* h, const float* const* src, const size_t* n_src, const float* const* tgt,
+                    const size_t* n_tgt, size_t batch, int with_fitness, b2icp_result* out, bool from_device) {
+  const bool shared_target = (tgt == nullptr);
+  if ((shared_target || !tgt[0]) && !gslot(h, 0).valid) return fail(h, B2ICP_ERR_NO_TARGET, "no target cloud set");
+  int worst = B2ICP_OK;
+  h->aligned = false;
+  ScanSlot& s = slot(h, 0);
+  for (size_t i = 0; i < batch; ++i) {
+    s.grid = 0;
+    if (!shared_target && (tgt[i] || i > 0)) {
+      GridSlot& g1 = gslot(h, 1);
+      size_t tn = 0;
+      if (tgt[i]) {
+        tn = n_tgt ? n_tgt[i] : 0;
+        int rc = upload_cloud(h, g1.tgt, tgt[i], tn, from_device);
+        if (rc) return rc;
+      } else {  // consecutive sweeps: the previous source becomes the target
+        std::swap(g1.tgt.raw, s.src.raw);
+        tn = g1.tgt.n = s.src.n;
+        g1.tgt.valid = true;
+        s.src.valid = false;
+      }
+      g1.pts = g1.tgt.raw.as<float4>();
+      GridSlot* gp = &g1;
+      int rc = build_grids(h, &gp, &tn, 1);
+      if (rc) return rc;
+      s.grid = 1;
+    }
+    int rc = upload_cloud(h, s.src, src[i], n_src[i], from_device);
+    if (rc) return rc;
+    rc = run_gicp(h, nullptr);
+    if (rc) {  // hard failure of this pair (too few points, CUDA): reported, the batch goes on
+      out[i].status_detail = rc;
+      if (worst == B2ICP_OK) worst = rc;
+      if (rc == B2ICP_ERR_CUDA) return rc;
+      continue;
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    fill_result(h->h_states[0], &out[i]);
+    const int status = h->h_states[0].status;
+    if (with_fitness && status == 0) {
+      rc = enqueue_fitness(h, 0, DBL_MAX);
+      if (rc) return rc;
+      CK(cudaMemcpyAsync(h->h_states, h->states.p, sizeof(IcpState), cudaMemcpyDeviceToHost, h->stream));
+      CK(cudaStreamSynchronize(h->stream));
+      out[i].fitness = fitness_value(h->h_states[0]);
+    }
+    if (status != 0 && worst == B2ICP_OK) {
+      worst = status;
+      h->err = status_message(worst);
+    }
+  }
+  CK(cudaGetLastError());
+  return worst;
+}
+
 int batch_impl(b2icp_handle* h, const float* const* src, const size_t* n_src, const float* const* tgt,
                const size_t* n_tgt, size_t batch, int with_fitness, b2icp_result* out, bool from_device) {
   for (size_t i = 0; i < batch; ++i) identity_result(&out[i]);
   if (batch == 0) return B2ICP_OK;
-  if (h->params.mode != B2ICP_MODE_P2P_SVD)
-    return fail(h, B2ICP_ERR_INVALID_ARG, "b2icp_align_batch runs the point-to-point mode only; use b2icp_align for GICP");
   const bool shared_target = (tgt == nullptr);
+  if (h->params.mode == B2ICP_MODE_GICP_BFGS) return gicp_batch_impl(h, src, n_src, tgt, n_tgt, batch, with_fitness, out, from_device);
   if (shared_target && !gslot(h, 0).valid) return fail(h, B2ICP_ERR_NO_TARGET, "no target cloud set");
   if (!shared_target && !tgt[0] && !gslot(h, 0).valid) return fail(h, B2ICP_ERR_NO_TARGET, "pair 0 has no target");
   int worst = B2ICP_OK;

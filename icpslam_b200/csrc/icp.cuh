@@ -225,7 +225,25 @@ __global__ void __launch_bounds__(kSweepThreads) fitness_kernel(const ScanTask* 
   const float4 p = __ldg(t.src + i);
   const float4 q = xform_f(sT, p.x, p.y, p.z);
   q_out[i] = q;
-  NNResult r = grid_nn<kSweepThreads>(t.grid, q.x, q.y, q.z, INFINITY, max_rings, -1, sc);
+  unsigned long long seed = kInfKey;
+  if (t.pad) {
+    // the point-to-point loop left its certificate (nncache.cuh) for cur[i], which is final_T * src[i] up to
+    // the last increment and float rounding: the same triangle-inequality test settles most queries here too
+    const float4 c = t.cur[i], c0 = t.c0[i], c1 = t.c1[i];
+    const float step = __fmul_ru(sqrt_fast(sqdist3(q.x, q.y, q.z, c.x, c.y, c.z)), kRelUp);
+    const float L = __fsub_rd(t.lb[i], step);
+    const int i0 = __float_as_int(c0.w), i1 = __float_as_int(c1.w);
+    const unsigned long long k0 = i0 >= 0 ? pack_key(sqdist3(q.x, q.y, q.z, c0.x, c0.y, c0.z), i0) : kInfKey;
+    const unsigned long long k1 = i1 >= 0 ? pack_key(sqdist3(q.x, q.y, q.z, c1.x, c1.y, c1.z), i1) : kInfKey;
+    seed = k1 < k0 ? k1 : k0;
+    const float L2 = L > 0.0f ? __fmul_rd(__fmul_rd(L, L), kRelDown) : 0.0f;
+    if (key_d2(seed) < L2) {
+      idx_out[i] = key_idx(seed);
+      d2_out[i] = key_d2(seed);
+      return;
+    }
+  }
+  NNResult r = grid_nn<kSweepThreads>(t.grid, q.x, q.y, q.z, INFINITY, max_rings, -1, sc, seed);
   if (!r.resolved) {
     unsigned int slot = atomicAdd(unresolved_count, 1u);
     unresolved_list[slot] = i;

@@ -63,10 +63,12 @@ __device__ __forceinline__ void scan_range(const float4* __restrict__ pts, int s
 }
 
 // `seed_pos` >= 0: sorted position of a target point already known to be close (the previous
-// iteration's match).  It only tightens the pruning threshold; the result is still the exact NN.
+// iteration's match); `seed_key`: the packed (d2, index) of such a point when only its value is known.
+// Either only tightens the pruning threshold; the result is still the exact NN.
 template <int THREADS>
 __device__ __forceinline__ NNResult grid_nn(const GridView& g, float qx, float qy, float qz, float bound2,
-                                            int max_rings, int seed_pos, NNScratch<THREADS>& sc) {
+                                            int max_rings, int seed_pos, NNScratch<THREADS>& sc,
+                                            unsigned long long seed_key = kInfKey) {
   NNResult r;
   r.key = kInfKey;
   r.pos = -1;
@@ -81,6 +83,10 @@ __device__ __forceinline__ NNResult grid_nn(const GridView& g, float qx, float q
     const float4 p = __ldg(g.pts + seed_pos);
     r.key = pack_key(sqdist3(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w));
     r.pos = seed_pos;
+  }
+  if (seed_key < r.key) {  // a candidate known by value (d2, index) only: tightens the threshold the same way
+    r.key = seed_key;
+    r.pos = -1;
   }
   // ---- phase 0: own cell
   scan_range(g.pts, s_own, e_own, qx, qy, qz, r.key, r.pos);

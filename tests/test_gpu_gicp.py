@@ -86,3 +86,24 @@ def test_gicp_kat_and_errors(R, oracle):
     with pytest.raises(R.B2icpError) as e:
         reg.align()
     assert e.value.code == -4 and not reg.hasConverged()
+
+
+def test_gicp_batch_equals_single_calls(R, oracle):
+    """b2icp_align_batch in GICP mode (consecutive sweeps: pair i registers against sweep i-1, and an explicit
+    target for pair 0) gives exactly what b2icp_align gives pair by pair, fitness included."""
+    _, _, sw = synth.sweep_sequence(2, 4, n_beams=64, n_az=128)
+    reg = R.Registration(preset=R.PRESET_ODOMETER, mode=R.MODE_GICP_BFGS)
+    rc, res = reg.alignBatch(sw[1:], [sw[0], None, None], with_fitness=True)
+    assert rc == 0 and len(res) == 3
+    for i in range(3):
+        one = R.Registration(preset=R.PRESET_ODOMETER, mode=R.MODE_GICP_BFGS)
+        one.setInputSource(sw[i + 1])
+        one.setInputTarget(sw[i])
+        one.align()
+        assert np.array_equal(res[i].matrix(), one.getFinalTransformation())
+        assert res[i].iterations == one.iterations and res[i].converged == int(one.hasConverged())
+        assert abs(res[i].fitness - one.getFitnessScore()) <= 1e-12
+    # shared target
+    reg.setInputTarget(sw[0])
+    rc, res2 = reg.alignBatch([sw[1], sw[1]], None)
+    assert rc == 0 and np.array_equal(res2[0].matrix(), res[0].matrix()) and np.array_equal(res2[1].matrix(), res[0].matrix())
