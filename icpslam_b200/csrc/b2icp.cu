@@ -135,6 +135,14 @@ struct b2icp_handle {
   std::vector<cudaEvent_t> events;
   b2icp_timing timing;
   long long launches = 0;
+  // streaming batches (b2icp_align_batch_submit / _wait): two sets of kMaxBatch / 2 slots
+  struct Pending {
+    int set, B, with_fitness;
+  };
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t set_uploaded[2] = {nullptr, nullptr}, set_done[2] = {nullptr, nullptr};
+  Pending pending[2] = {};
+  int n_pending = 0, first_pending = 0, next_set = 0;
   int qpt_override = 0;  // B2ICP_QPT environment variable (tuning only)
   std::vector<int> qpt_sched;  // B2ICP_QPT_SCHED="2,4,8": slab length per iteration, last value repeats (tuning only)
   double* h_gicp_partials = nullptr;  // pinned read-back of gicp_fdf_kernel's per-CTA sums
@@ -321,12 +329,12 @@ int build_grids(b2icp_handle* h, GridSlot* const* g, const size_t* n, int count)
   return B2ICP_OK;
 }
 
-int upload_cloud(b2icp_handle* h, Cloud& c, const float* xyzw, size_t n, bool from_device) {
+int upload_cloud(b2icp_handle* h, Cloud& c, const float* xyzw, size_t n, bool from_device, cudaStream_t on = nullptr) {
   if (!xyzw || n == 0) return fail(h, B2ICP_ERR_EMPTY_CLOUD, "empty cloud");
   if (n > (size_t)INT32_MAX / 8) return fail(h, B2ICP_ERR_INVALID_ARG, "cloud too large");
   CK(c.raw.ensure(n * sizeof(float4)));
   CK(cudaMemcpyAsync(c.raw.p, xyzw, n * sizeof(float4), from_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
-                     h->stream));
+                     on ? on : h->stream));
   c.n = n;
   c.valid = true;
   return B2ICP_OK;
@@ -379,18 +387,18 @@ void fill_result(const IcpState& s, b2icp_result* out) {
 
 // Advance slots [0, B) to convergence: one fused sweep launch per iteration for the whole batch.
 // guesses: B x 16 floats or NULL.  Results are read back by read_states().
-int run_batch(b2icp_handle* h, int B, const float* guesses) {
+int run_batch(b2icp_handle* h, int B, const float* guesses, int slot0 = 0, bool allow_prof = true) {
   if (h->params.mode != B2ICP_MODE_P2P_SVD) return fail(h, B2ICP_ERR_INVALID_ARG, "mode not implemented");
   size_t max_n = 0;
   double min_cell = 1e300;
   for (int i = 0; i < B; ++i) {
-    ScanSlot& s = slot(h, i);
+    ScanSlot& s = slot(h, (size_t)(slot0 + i));
     GridSlot& g = gslot(h, s.grid);
     int rc = ensure_slot_work(h, s);
     if (rc) return rc;
     max_n = std::max(max_n, s.src.n);
     min_cell = std::min(min_cell, (double)g.view.cell);
-    ScanTask& t = h->h_tasks[i];
+    ScanTask& t = h->h_tasks[slot0 + i];
     t.grid = g.view;
     t.src = s.src.raw.as<float4>();
     t.cur = s.cur.as<float4>();
@@ -401,10 +409,10 @@ int run_batch(b2icp_handle* h, int B, const float* guesses) {
     t.c1 = s.c1.as<float4>();
     t.lb = s.lb.as<float>();
     t.partials = s.partials.as<double>();
-    t.state = h->states.as<IcpState>() + i;
+    t.state = h->states.as<IcpState>() + slot0 + i;
     t.n = (int)s.src.n;
     t.pad = 1;  // the loop leaves a certificate per query: getFitnessScore starts from it
-    IcpState& st = h->h_states[i];
+    IcpState& st = h->h_states[slot0 + i];
     std::memset(&st, 0, sizeof(st));
     for (int k = 0; k < 16; ++k) {
       const float v = guesses ? guesses[16 * i + k] : ((k % 5 == 0) ? 1.f : 0.f);
@@ -415,10 +423,10 @@ int run_batch(b2icp_handle* h, int B, const float* guesses) {
     st.prev_mse = DBL_MAX;
   }
   h->cfg.max_rings = rings_for_bound(h, min_cell) + (int)std::ceil(h->cfg.margin_frac) + 1;
-  CK(cudaMemcpyAsync(h->tasks.p, h->h_tasks, sizeof(ScanTask) * B, cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemcpyAsync(h->states.p, h->h_states, sizeof(IcpState) * B, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->tasks.as<ScanTask>() + slot0, h->h_tasks + slot0, sizeof(ScanTask) * B, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->states.as<IcpState>() + slot0, h->h_states + slot0, sizeof(IcpState) * B, cudaMemcpyHostToDevice, h->stream));
 
-  const bool prof = h->params.profile != 0;
+  const bool prof = allow_prof && h->params.profile != 0;
   const int iters = std::max(h->params.max_iterations, 1);
   if (prof) {
     while ((int)h->events.size() < 2 * iters + 2) {
@@ -448,18 +456,18 @@ int run_batch(b2icp_handle* h, int B, const float* guesses) {
     const int q = qpt_at(it);
     const dim3 grid((unsigned)((max_n + (size_t)kSweepThreads * q - 1) / ((size_t)kSweepThreads * q)), (unsigned)B, 1);
     if (q == 8)
-      icp_sweep_p2p<8><<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>(), h->cfg);
+      icp_sweep_p2p<8><<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
     else if (q == 4)
-      icp_sweep_p2p<4><<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>(), h->cfg);
+      icp_sweep_p2p<4><<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
     else if (q == 2)
-      icp_sweep_p2p<2><<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>(), h->cfg);
+      icp_sweep_p2p<2><<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
     else
-      icp_sweep_p2p<1><<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>(), h->cfg);
+      icp_sweep_p2p<1><<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
     if (prof) CK(cudaEventRecord(h->events[3 + 2 * it], h->stream));
   }
   {  // correspondences of the last sweep, for b2icp_get_correspondences
     const dim3 fgrid((unsigned)((max_n + 255) / 256), (unsigned)B, 1);
-    icp_finalize_corr<<<fgrid, 256, 0, h->stream>>>(h->tasks.as<ScanTask>(), h->cfg);
+    icp_finalize_corr<<<fgrid, 256, 0, h->stream>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
   }
   h->launches += iters + 1;
   if (prof) CK(cudaEventRecord(h->events[1], h->stream));
@@ -787,6 +795,14 @@ int b2icp_destroy(b2icp_handle* h) {
                        &h->xf_out, &h->mat})
     b->release();
   for (cudaEvent_t e : h->events) cudaEventDestroy(e);
+  for (int k = 0; k < 2; ++k) {
+    if (h->set_uploaded[k]) cudaEventDestroy(h->set_uploaded[k]);
+    if (h->set_done[k]) cudaEventDestroy(h->set_done[k]);
+  }
+  if (h->copy_stream) {
+    cudaStreamSynchronize(h->copy_stream);
+    cudaStreamDestroy(h->copy_stream);
+  }
   if (h->h_states) cudaFreeHost(h->h_states);
   if (h->h_tasks) cudaFreeHost(h->h_tasks);
   if (h->h_bbox) cudaFreeHost(h->h_bbox);
@@ -1024,6 +1040,93 @@ int b2icp_align_batch(b2icp_handle* h, const float* const* src, const size_t* n_
   std::lock_guard<std::mutex> lk(h->mu);
   CK(cudaSetDevice(h->device));
   return batch_impl(h, src, n_src, tgt, n_tgt, batch, with_fitness, out, false);
+}
+
+// ---- streaming batches: two slot sets, uploads of batch k+1 overlap the sweeps of batch k ----------------
+static int submit_impl(b2icp_handle* h, const float* const* src, const size_t* n_src, size_t batch, int with_fitness,
+                       bool from_device);
+int b2icp_align_batch_submit(b2icp_handle* h, const float* const* src, const size_t* n_src, size_t batch, int with_fitness) {
+  if (!h || !src || !n_src) return B2ICP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CK(cudaSetDevice(h->device));
+  return submit_impl(h, src, n_src, batch, with_fitness, false);
+}
+int b2icp_align_batch_submit_device(b2icp_handle* h, const float* const* d_src, const size_t* n_src, size_t batch,
+                                    int with_fitness) {
+  if (!h || !d_src || !n_src) return B2ICP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CK(cudaSetDevice(h->device));
+  return submit_impl(h, d_src, n_src, batch, with_fitness, true);
+}
+static int submit_impl(b2icp_handle* h, const float* const* src, const size_t* n_src, size_t batch, int with_fitness,
+                       bool from_device) {
+  if (h->params.mode != B2ICP_MODE_P2P_SVD) return fail(h, B2ICP_ERR_INVALID_ARG, "streaming batches run the point-to-point mode only");
+  if (batch == 0 || batch > (size_t)kMaxBatch / 2) return fail(h, B2ICP_ERR_INVALID_ARG, "a streamed batch holds 1..32 scans");
+  if (!gslot(h, 0).valid) return fail(h, B2ICP_ERR_NO_TARGET, "no target cloud set");
+  if (h->n_pending >= 2) return fail(h, B2ICP_ERR_INVALID_ARG, "two batches are already in flight: call b2icp_align_batch_wait");
+  if (!h->copy_stream) {
+    CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+      CK(cudaEventCreateWithFlags(&h->set_uploaded[k], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&h->set_done[k], cudaEventDisableTiming));
+    }
+  }
+  const int set = h->next_set;
+  const int slot0 = set * (kMaxBatch / 2);
+  const int B = (int)batch;
+  h->aligned = false;
+  for (int i = 0; i < B; ++i) {
+    ScanSlot& s = slot(h, (size_t)(slot0 + i));
+    s.grid = 0;
+    int rc = upload_cloud(h, s.src, src[i], n_src[i], from_device, h->copy_stream);
+    if (rc) {
+      cudaStreamSynchronize(h->copy_stream);
+      return rc;
+    }
+  }
+  CK(cudaEventRecord(h->set_uploaded[set], h->copy_stream));
+  CK(cudaStreamWaitEvent(h->stream, h->set_uploaded[set], 0));
+  int rc = run_batch(h, B, nullptr, slot0, false);
+  if (rc) return rc;
+  if (with_fitness)
+    for (int i = 0; i < B; ++i) {
+      rc = enqueue_fitness(h, slot0 + i, DBL_MAX);
+      if (rc) return rc;
+    }
+  CK(cudaMemcpyAsync(h->h_states + slot0, h->states.as<IcpState>() + slot0, sizeof(IcpState) * B, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaEventRecord(h->set_done[set], h->stream));
+  h->pending[(h->first_pending + h->n_pending) % 2] = {set, B, with_fitness};
+  h->n_pending += 1;
+  h->next_set ^= 1;
+  return B2ICP_OK;
+}
+
+int b2icp_align_batch_wait(b2icp_handle* h, b2icp_result* out, size_t capacity, size_t* n_out) {
+  if (!h || !out) return B2ICP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CK(cudaSetDevice(h->device));
+  if (n_out) *n_out = 0;
+  if (h->n_pending == 0) return fail(h, B2ICP_ERR_INVALID_ARG, "no streamed batch in flight");
+  const b2icp_handle::Pending pd = h->pending[h->first_pending];
+  if (capacity < (size_t)pd.B) return fail(h, B2ICP_ERR_INVALID_ARG, "result buffer too small");
+  CK(cudaEventSynchronize(h->set_done[pd.set]));
+  CK(cudaGetLastError());
+  h->first_pending ^= 1;
+  h->n_pending -= 1;
+  const int slot0 = pd.set * (kMaxBatch / 2);
+  int worst = B2ICP_OK;
+  for (int i = 0; i < pd.B; ++i) {
+    const IcpState& st = h->h_states[slot0 + i];
+    fill_result(st, &out[i]);
+    if (pd.with_fitness && st.status == 0) out[i].fitness = fitness_value(st);
+    if (st.status != 0 && worst == B2ICP_OK) {
+      worst = st.status;
+      h->err = status_message(worst);
+    }
+  }
+  h->timing.kernel_launches = h->launches;
+  if (n_out) *n_out = (size_t)pd.B;
+  return worst;
 }
 
 int b2icp_align_batch_device(b2icp_handle* h, const float* const* d_src, const size_t* n_src,

@@ -41,6 +41,11 @@ __device__ __forceinline__ float sqrt_fast(float x) {
   return y;
 }
 
+#ifndef B2_PREFETCH_RUNS
+#define B2_PREFETCH_RUNS 0  /* measured: no gain (10 294 vs 10 571 scans/s), the runs are mostly L1 hits already */
+#endif
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 struct Top3 {
   unsigned long long k0;  // best (d2, original index)
   int p0;                 // its sorted position, -1 = none
@@ -166,6 +171,11 @@ __device__ __forceinline__ void box_search(const GridView& g, float qx, float qy
         sc.start[nlist][tid] = s;
         sc.meta[nlist][tid] = (unsigned)e;
         ++nlist;
+#if B2_PREFETCH_RUNS
+        // request the run's lines now: the scan below would otherwise pay one L2 round trip per run, in turn
+        prefetch_l1(g.pts + s);
+        if (e - s > 8) prefetch_l1(g.pts + s + 8);
+#endif
       }
     }
     int li = 0, j = 0, e = 0;

@@ -92,6 +92,7 @@ EXPORTS = [
     "b2icp_align", "b2icp_fitness", "b2icp_get_correspondences", "b2icp_nn_search", "b2icp_nn_search_device",
     "b2icp_transform_cloud", "b2icp_transform_cloud_f", "b2icp_align_batch", "b2icp_align_batch_device",
     "b2icp_set_stream", "b2icp_compute_covariances", "b2icp_voxel_filter", "b2icp_get_timing",
+    "b2icp_align_batch_submit", "b2icp_align_batch_submit_device", "b2icp_align_batch_wait",
     "b2icp_map_reset", "b2icp_map_insert", "b2icp_map_insert_device", "b2icp_map_size", "b2icp_map_download",
     "b2icp_map_nearest", "b2icp_set_target_map",
     "b2icp_get_grid_info", "b2icp_host_alloc", "b2icp_host_free", "b2icp_last_error", "b2icp_status_string",
@@ -136,6 +137,9 @@ def load_library() -> C.CDLL:
     L.b2icp_compute_covariances.argtypes = [vp, vp, C.c_size_t, dp]
     L.b2icp_voxel_filter.argtypes = [vp, vp, C.c_size_t, C.c_float, vp, C.POINTER(C.c_size_t)]
     szp = C.POINTER(C.c_size_t)
+    L.b2icp_align_batch_submit.argtypes = [vp, vp, vp, C.c_size_t, C.c_int]
+    L.b2icp_align_batch_submit_device.argtypes = [vp, vp, vp, C.c_size_t, C.c_int]
+    L.b2icp_align_batch_wait.argtypes = [vp, vp, C.c_size_t, szp]
     L.b2icp_map_reset.argtypes = [vp, C.c_double]
     L.b2icp_map_insert.argtypes = [vp, vp, C.c_size_t, szp]
     L.b2icp_map_insert_device.argtypes = [vp, vp, C.c_size_t, szp]
@@ -354,6 +358,40 @@ class Registration:
         rc = self._L.b2icp_align_batch(self._h, sp, sn, tp, tn, n, 1 if with_fitness else 0, res)
         self._n_source = len(srcs[0]) if srcs else 0
         return rc, list(res)
+
+    def alignBatchSubmit(self, sources, with_fitness: bool = False) -> int:
+        """b2icp_align_batch_submit: enqueue up to 32 host clouds (page-locked ones overlap best) against the
+        current target and return at once; at most two batches in flight.  Pair with alignBatchWait()."""
+        n = len(sources)
+        srcs = [_cloud(s) for s in sources]
+        sp = (C.c_void_p * n)(*[s.ctypes.data for s in srcs])
+        sn = (C.c_size_t * n)(*[len(s) for s in srcs])
+        rc = self._L.b2icp_align_batch_submit(self._h, sp, sn, n, 1 if with_fitness else 0)
+        if rc == 0:
+            self._inflight = getattr(self, "_inflight", []) + [(srcs, n)]  # keep the host buffers alive
+        return rc
+
+    def alignBatchSubmitDevice(self, src_ptrs, n_src, with_fitness: bool = False) -> int:
+        """b2icp_align_batch_submit_device: same, the clouds already live in device memory."""
+        n = len(src_ptrs)
+        sp = (C.c_void_p * n)(*src_ptrs)
+        sn = (C.c_size_t * n)(*n_src)
+        rc = self._L.b2icp_align_batch_submit_device(self._h, sp, sn, n, 1 if with_fitness else 0)
+        if rc == 0:
+            self._inflight = getattr(self, "_inflight", []) + [(None, n)]
+        return rc
+
+    def alignBatchWait(self):
+        """b2icp_align_batch_wait: (rc, results) of the oldest batch in flight."""
+        pend = getattr(self, "_inflight", [])
+        if not pend:
+            raise B2icpError(-1, "alignBatchWait: no batch in flight")
+        _, n = pend[0]
+        res = (Result * n)()
+        got = C.c_size_t()
+        rc = self._L.b2icp_align_batch_wait(self._h, res, n, C.byref(got))
+        self._inflight = pend[1:]
+        return rc, list(res)[: got.value]
 
     def alignBatchDevice(self, src_ptrs, n_src, with_fitness: bool = False):
         """b2icp_align_batch_device against the current target; src_ptrs are device addresses."""

@@ -195,6 +195,17 @@ int b2icp_compute_covariances(b2icp_handle* h, const float* xyzw, size_t n, doub
 int b2icp_voxel_filter(b2icp_handle* h, const float* in_xyzw, size_t n, float leaf, float* out_xyzw,
                        size_t* n_out);
 
+/* Streaming form of b2icp_align_batch for host clouds against the handle's current target (point-to-point
+ * mode): _submit enqueues the uploads of up to 32 scans on a copy stream and their ICP loops behind them and
+ * returns at once; _wait blocks until the OLDEST submitted batch is done and writes its results (*n_out of them,
+ * in submission order).  Two batches may be in flight, so the PCIe transfer of batch k+1 overlaps the sweeps of
+ * batch k.  The host clouds of a batch must stay valid (and should be page-locked, b2icp_host_alloc) until its
+ * _wait returns.  The synchronous calls must not be mixed in while batches are in flight. */
+int b2icp_align_batch_submit(b2icp_handle* h, const float* const* src, const size_t* n_src, size_t batch, int with_fitness);
+int b2icp_align_batch_submit_device(b2icp_handle* h, const float* const* d_src, const size_t* n_src, size_t batch,
+                                    int with_fitness);
+int b2icp_align_batch_wait(b2icp_handle* h, b2icp_result* out, size_t capacity, size_t* n_out);
+
 /* ---- the mapper's point map (OctreeMapper::map_octree_ / map_cloud_, octree_mapper.h:82-83) --------------
  * b2icp_map_reset          OctreeMapper::resetMap (octree_mapper.cpp:56-60): empty map at `resolution`.
  * b2icp_map_insert         OctreeMapper::addPointsToMap (octree_mapper.cpp:63-71): a point enters the map iff

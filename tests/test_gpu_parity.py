@@ -409,6 +409,35 @@ def test_batch_shared_target_equals_single_calls(R, oracle):
     assert_transform_close(res[1].matrix(), o["T"])
 
 
+def test_streamed_batches_equal_synchronous_batches(R):
+    """b2icp_align_batch_submit / _wait (two slot sets, uploads on a copy stream) return, batch by batch and in
+    submission order, exactly what b2icp_align_batch returns."""
+    _, _, sw = synth.sweep_sequence(3, 9, n_beams=64, n_az=128)
+    reg = R.Registration(preset=R.PRESET_MAPPER)
+    reg.setInputTarget(sw[0])
+    batches = [sw[1:4], sw[4:6], sw[6:9], sw[2:5]]
+    rc, ref = reg.alignBatch([s for b in batches for s in b], None, with_fitness=True)
+    assert rc == 0
+    got = []
+    assert reg.alignBatchSubmit(batches[0], with_fitness=True) == 0
+    for k in range(1, len(batches)):
+        assert reg.alignBatchSubmit(batches[k], with_fitness=True) == 0      # two in flight
+        rc, res = reg.alignBatchWait()                                       # the older one
+        assert rc == 0
+        got += res
+    rc, res = reg.alignBatchWait()
+    assert rc == 0
+    got += res
+    assert len(got) == len(ref)
+    for a, b in zip(got, ref):
+        assert np.array_equal(a.matrix(), b.matrix()) and a.iterations == b.iterations
+        assert a.fitness == b.fitness and a.n_corr_last == b.n_corr_last
+    assert reg.alignBatchSubmit(batches[0]) == 0
+    assert reg.alignBatchSubmit(batches[1]) == 0
+    assert reg.alignBatchSubmit(batches[2]) != 0                             # a third batch in flight is refused
+    assert reg.alignBatchWait()[0] == 0 and reg.alignBatchWait()[0] == 0
+
+
 def test_batch_consecutive_pairs_longer_than_one_chunk(R, oracle):
     """tgt[i] == NULL: pair i registers against src[i-1]; 70 pairs cross the 64-slot chunk border."""
     _, _, sw = synth.sweep_sequence(6, 6, n_beams=32, n_az=128)
