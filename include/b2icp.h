@@ -198,9 +198,11 @@ int b2icp_voxel_filter(b2icp_handle* h, const float* in_xyzw, size_t n, float le
 /* Streaming form of b2icp_align_batch for host clouds against the handle's current target (point-to-point
  * mode): _submit enqueues the uploads of up to 32 scans on a copy stream and their ICP loops behind them and
  * returns at once; _wait blocks until the OLDEST submitted batch is done and writes its results (*n_out of them,
- * in submission order).  Two batches may be in flight, so the PCIe transfer of batch k+1 overlaps the sweeps of
- * batch k.  The host clouds of a batch must stay valid (and should be page-locked, b2icp_host_alloc) until its
+ * in submission order).  Up to B2ICP_MAX_IN_FLIGHT batches may be in flight (each on its own stream), so the PCIe
+ * transfer of the next batches overlaps the sweeps of the current one and the sparse late iterations of one batch
+ * share the device with the first iterations of the next.  The host clouds of a batch must stay valid (and should be page-locked, b2icp_host_alloc) until its
  * _wait returns.  The synchronous calls must not be mixed in while batches are in flight. */
+#define B2ICP_MAX_IN_FLIGHT 4
 int b2icp_align_batch_submit(b2icp_handle* h, const float* const* src, const size_t* n_src, size_t batch, int with_fitness);
 int b2icp_align_batch_submit_device(b2icp_handle* h, const float* const* d_src, const size_t* n_src, size_t batch,
                                     int with_fitness);

@@ -432,10 +432,16 @@ def test_streamed_batches_equal_synchronous_batches(R):
     for a, b in zip(got, ref):
         assert np.array_equal(a.matrix(), b.matrix()) and a.iterations == b.iterations
         assert a.fitness == b.fitness and a.n_corr_last == b.n_corr_last
-    assert reg.alignBatchSubmit(batches[0]) == 0
-    assert reg.alignBatchSubmit(batches[1]) == 0
-    assert reg.alignBatchSubmit(batches[2]) != 0                             # a third batch in flight is refused
-    assert reg.alignBatchWait()[0] == 0 and reg.alignBatchWait()[0] == 0
+    for k in range(4):
+        assert reg.alignBatchSubmit(batches[k]) == 0                         # four in flight, each on its own stream
+    assert reg.alignBatchSubmit(batches[0]) != 0                             # a fifth is refused
+    got = []
+    for k in range(4):
+        rc, res = reg.alignBatchWait()
+        assert rc == 0
+        got += res
+    for a, b in zip(got, ref):
+        assert np.array_equal(a.matrix(), b.matrix()) and a.iterations == b.iterations
 
 
 def test_batch_consecutive_pairs_longer_than_one_chunk(R, oracle):
