@@ -531,10 +531,13 @@ extern "C" {
 
 int b2o_set_threads(int n) {
 #ifdef _OPENMP
-  int mx = omp_get_max_threads();
+  /* the cores this process may run on, not OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1 to its workers,
+   * which would silently turn the "all host threads" baseline into a single-thread one) */
+  int mx = omp_get_num_procs();
   if (n < 1) n = 1;
   if (n > mx) n = mx;
   g_threads = n;
+  omp_set_dynamic(0);
 #else
   (void)n;
   g_threads = 1;

@@ -409,6 +409,26 @@ def test_batch_shared_target_equals_single_calls(R, oracle):
     assert_transform_close(res[1].matrix(), o["T"])
 
 
+def test_ragged_batch_and_tiny_sources(R, oracle):
+    """Scans of very different sizes in one batch (5 ... 16384 points: slabs with a partial warp, warps past the
+    end, a source too small to register) give what the oracle gives scan by scan."""
+    _, _, sw = synth.sweep_sequence(5, 2, n_beams=64, n_az=256)
+    tgt, full = sw[0], sw[1]
+    sizes = [16384, 1000, 37, 33, 32, 31, 5, 2, 4097]
+    srcs = [np.ascontiguousarray(full[:: max(1, len(full) // n)][:n]) for n in sizes]
+    reg = R.Registration(preset=R.PRESET_MAPPER)
+    reg.setInputTarget(tgt)
+    rc, res = reg.alignBatch(srcs, None, with_fitness=True)
+    p = oracle.default_params("mapper")
+    for s, r in zip(srcs, res):
+        o = oracle.align(p, s, tgt)
+        assert r.iterations == o["iterations"] and r.converged == int(o["converged"]), len(s)
+        assert r.status_detail == o["rc"], (len(s), r.status_detail, o["rc"])
+        if o["rc"] == 0:
+            assert_transform_close(r.matrix(), o["T"])
+    assert rc == -4 and res[7].status_detail == -4          # 2 points: PCL's "not enough correspondences"
+
+
 def test_streamed_batches_equal_synchronous_batches(R):
     """b2icp_align_batch_submit / _wait (two slot sets, uploads on a copy stream) return, batch by batch and in
     submission order, exactly what b2icp_align_batch returns."""
