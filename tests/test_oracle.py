@@ -202,3 +202,22 @@ def test_gicp_is_roundoff_sensitive(oracle):
         assert d < 1e-2
         worst = max(worst, d)
     assert worst > 1e-5
+
+
+def test_map_insert_matches_numpy_restatement(oracle):
+    """OctreeMapper::addPointsToMap (reference src/icpslam/octree_mapper.cpp:63-71): one point per voxel, first
+    come wins, insertion order kept — the oracle against an independent numpy restatement, incrementally."""
+    _, poses, sw = synth.sweep_sequence(9, 3, n_beams=32, n_az=256)
+    res = 0.2
+    world = [synth.as_xyzw(s[:, :3].astype(np.float64) @ T[:3, :3].T + T[:3, 3]) for s, T in zip(sw, poses)]
+    m = np.zeros((0, 4), np.float32)
+    for w in world:
+        m = np.concatenate([m, oracle.map_insert(m, w, res)])
+    allp = np.concatenate(world)
+    ref = synth.voxel_dedup_first(allp, res)
+    assert np.array_equal(m[:, :3], ref[:, :3]) and np.all(m[:, 3] == 1.0)
+    key = np.floor(m[:, :3].astype(np.float64) / res).astype(np.int64)
+    assert len(np.unique(key, axis=0)) == len(m)                       # at most one point per voxel
+    assert len(oracle.map_insert(m, allp, res)) == 0                   # idempotent
+    bad = np.array([[np.nan, 0, 0, 1], [1e3, 1e3, 1e3, 1]], np.float32)
+    assert np.array_equal(oracle.map_insert(m, bad, res), bad[1:])     # non-finite points are skipped
