@@ -1,17 +1,18 @@
 // icp.cuh — K2+K3+K4 fused: one launch = one ICP iteration of pcl::IterativeClosestPoint
 // (SURVEY.md App. A.3), for every scan of a batch (blockIdx.y).
 //
-//   per thread   q = transformation_ * q          (in-place float chain, exactly PCL's
+//   per query    q = transformation_ * q          (in-place float chain, exactly PCL's
 //                                                  transformCloud(input_transformed, ..., in place))
-//                exact 1-NN in the target grid    (nn.cuh)
+//                exact 1-NN in the target grid    (cached-neighbour certificate, else box search: nncache.cuh)
 //                gate  d2 <= max_dist^2           (CorrespondenceEstimation keeps equality)
-//                16 running sums + sum(d2)        (fp64 accumulators)
-//   per CTA      warp-shuffle reduction, then a fixed-order cross-warp sum -> partials[cta][17]
-//   last CTA     fixed-order tree over the per-CTA partials (deterministic), Umeyama/SVD,
+//                16 running sums + sum(d2)        (fp64 accumulators of the lane that settled the query)
+//   per warp     xor-butterfly -> partials[slab][17]
+//   last warp    fixed-order sum over the slabs' partials (deterministic), Umeyama/SVD,
 //                final = T * final, DefaultConvergenceCriteria -> IcpState (solve.cuh)
 // No host round trip: `done` in IcpState turns the remaining launches of the batch into no-ops.
-// HBM/L2 bytes per query per iteration: 16 read + 16 write (running cloud) + 8 write (idx, d2)
-// + the target points of the touched cells; the reduction adds 136 B per CTA.
+// HBM bytes per query per iteration: 52 read (running point, two cached neighbours, bound) + 20 written
+// (running point, bound), + 36 written and the target points of the scanned cells when the query is searched;
+// the reduction adds 136 B per warp.  Also here: getFitnessScore, the correspondence write-out, transformPointCloud.
 #pragma once
 #include "common.cuh"
 #include "nn.cuh"
