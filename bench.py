@@ -231,7 +231,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="sweeps per GPU per step")
     ap.add_argument("--impl", default="b2icp", choices=["b2icp", "reference"])
     ap.add_argument("--cpu-sample", type=int, default=4, help="sweeps timed on the CPU oracle (rank 0, N=1)")
-    ap.add_argument("--in-flight", type=int, default=4, help="streamed batches in flight (1..4)")
+    ap.add_argument("--in-flight", type=int, default=8, help="streamed batches in flight (1..8)")
     ap.add_argument("--grid-cell", type=float, default=0.0, help="neighbour-grid cell edge in metres (0 = auto); tuning only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b2icp" else args.warmup
@@ -368,7 +368,7 @@ def main():
             done += 1
 
     def timed_streamed(submit, steps, warmup):
-        run_streamed(max(warmup, 4), submit)  # every one of the library's 4 slot sets allocates its buffers once
+        run_streamed(max(warmup, 8), submit)  # every one of the library's 8 slot sets allocates its buffers once
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()

@@ -46,7 +46,7 @@ constexpr double kMaxOccupancy = 4.0;     // above this the grid is rebuilt with
 constexpr float kCacheMarginFrac = 0.05f;  // nncache.cuh: box-search margin as a fraction of the cell edge
 constexpr int kFirstSweepQpt = 2;         // slab length (x 32 queries per warp) of the first sweep of a batch
 constexpr int kMaxBatch = 64;             // scans advanced together by one sweep launch
-constexpr int kStreamSets = 4;            // streamed batches in flight (b2icp_align_batch_submit / _wait)
+constexpr int kStreamSets = 8;            // streamed batches in flight (b2icp_align_batch_submit / _wait)
 constexpr int kSetSlots = 32;             // scans per streamed batch
 constexpr int kSlots = kStreamSets * kSetSlots > kMaxBatch ? kStreamSets * kSetSlots : kMaxBatch;  // state / task records
 

@@ -361,7 +361,7 @@ class Registration:
 
     def alignBatchSubmit(self, sources, with_fitness: bool = False) -> int:
         """b2icp_align_batch_submit: enqueue up to 32 host clouds (page-locked ones overlap best) against the
-        current target and return at once; at most B2ICP_MAX_IN_FLIGHT (4) batches in flight.  Pair with alignBatchWait()."""
+        current target and return at once; at most B2ICP_MAX_IN_FLIGHT (8) batches in flight.  Pair with alignBatchWait()."""
         n = len(sources)
         srcs = [_cloud(s) for s in sources]
         sp = (C.c_void_p * n)(*[s.ctypes.data for s in srcs])

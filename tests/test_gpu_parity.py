@@ -452,15 +452,15 @@ def test_streamed_batches_equal_synchronous_batches(R):
     for a, b in zip(got, ref):
         assert np.array_equal(a.matrix(), b.matrix()) and a.iterations == b.iterations
         assert a.fitness == b.fitness and a.n_corr_last == b.n_corr_last
-    for k in range(4):
-        assert reg.alignBatchSubmit(batches[k]) == 0                         # four in flight, each on its own stream
-    assert reg.alignBatchSubmit(batches[0]) != 0                             # a fifth is refused
+    for k in range(8):
+        assert reg.alignBatchSubmit(batches[k % 4]) == 0                     # eight in flight, each on its own stream
+    assert reg.alignBatchSubmit(batches[0]) != 0                             # a ninth is refused
     got = []
-    for k in range(4):
+    for k in range(8):
         rc, res = reg.alignBatchWait()
         assert rc == 0
         got += res
-    for a, b in zip(got, ref):
+    for a, b in zip(got, ref + ref):
         assert np.array_equal(a.matrix(), b.matrix()) and a.iterations == b.iterations
 
 
