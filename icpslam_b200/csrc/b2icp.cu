@@ -1438,6 +1438,96 @@ int b2icp_map_nearest(b2icp_handle* h, const float* q_xyzw, size_t n, int32_t* i
   return B2ICP_OK;
 }
 
+// OctreeMapper::refineTransformAndGrowMap (octree_mapper.cpp:133-173) with the scan uploaded once and every
+// intermediate cloud left in device memory.
+int b2icp_mapper_register(b2icp_handle* h, const float* xyzw, size_t n, const float* T_raw, const float* T_raw_inv,
+                          b2icp_result* out) {
+  if (!h || !out) return B2ICP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CK(cudaSetDevice(h->device));
+  identity_result(out);
+  if (!xyzw || n == 0) return fail(h, B2ICP_ERR_EMPTY_CLOUD, "empty cloud");
+  if (!T_raw || !T_raw_inv) return fail(h, B2ICP_ERR_INVALID_ARG, "NULL pose matrix");
+  if (h->map_size == 0) return fail(h, B2ICP_ERR_NO_TARGET, "the map is empty");
+  h->aligned = false;
+  ScanSlot& s = slot(h, 0);
+  s.grid = 0;
+  int rc = upload_cloud(h, s.src, xyzw, n, false);  // icp.setInputSource(curr_cloud), kept for b2icp_mapper_grow
+  if (rc) return rc;
+  rc = map_ensure_grid(h);
+  if (rc) return rc;
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  CK(h->query.ensure(n * sizeof(float4)));
+  CK(h->q_idx.ensure((n + 8) * sizeof(int)));
+  CK(h->q_d2.ensure(n * sizeof(float)));
+  CK(h->map_flags.ensure((n + 8) * sizeof(int)));
+  CK(h->xf_in.ensure(n * sizeof(float4)));
+  CK(h->xf_out.ensure(n * sizeof(float4)));
+  CK(h->mat.ensure(32 * sizeof(float)));
+  CK(cudaMemcpyAsync(h->mat.p, T_raw, 16 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->mat.as<float>() + 16, T_raw_inv, 16 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  // line 136: cloud_in_map = raw_pose (x) cloud
+  transform_cloud_f<<<blocks, 256, 0, h->stream>>>(s.src.raw.as<float4>(), (int)n, h->mat.as<float>(), h->query.as<float4>());
+  // lines 145 / 73-90: the map point nearest to every scan point, compacted in scan order
+  rc = nn_search_impl(h, h->query.as<float4>(), n, h->q_idx.as<int>(), h->q_d2.as<float>(), (int)kMapGrid);
+  if (rc) return rc;
+  map_gather_flag<<<blocks, 256, 0, h->stream>>>(h->q_idx.as<int>(), (int)n, h->map_flags.as<int>());
+  int found = 0;
+  rc = scan_flags(h, h->map_flags.as<int>(), n, &found);
+  if (rc) return rc;
+  if (found == 0) return fail(h, B2ICP_ERR_NO_TARGET, "no map point near the scan");
+  map_gather<<<blocks, 256, 0, h->stream>>>(h->q_idx.as<int>(), (int)n, h->map_flags.as<int>(), h->map_pts.as<float4>(),
+                                            h->xf_in.as<float4>());
+  // line 149: nn_cloud = raw_pose^-1 (x) nn_cloud_in_map
+  transform_cloud_f<<<(unsigned)((found + 255) / 256), 256, 0, h->stream>>>(h->xf_in.as<float4>(), found, h->mat.as<float>() + 16,
+                                                                          h->xf_out.as<float4>());
+  h->launches += 4;
+  // lines 104-117: icp(source = cloud, target = nn_cloud)
+  rc = set_target_impl(h, 0, h->xf_out.as<float>(), (size_t)found, true);
+  if (rc) return rc;
+  const bool gicp = h->params.mode == B2ICP_MODE_GICP_BFGS;
+  rc = gicp ? run_gicp(h, nullptr) : run_batch(h, 1, nullptr);
+  if (rc) return rc;
+  if (gicp) {
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+  } else {
+    rc = read_states(h, 1);
+    if (rc) return rc;
+  }
+  fill_result(h->h_states[0], out);
+  h->aligned = true;
+  if (h->h_states[0].status != 0) {
+    h->err = status_message(h->h_states[0].status);
+    return h->h_states[0].status;
+  }
+  return B2ICP_OK;
+}
+
+int b2icp_mapper_grow(b2icp_handle* h, const float* xyzw, size_t n, const float* T, size_t* n_added) {
+  if (!h || !T) return B2ICP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CK(cudaSetDevice(h->device));
+  if (n_added) *n_added = 0;
+  ScanSlot& s = slot(h, 0);
+  if (xyzw) {
+    int rc = upload_cloud(h, s.src, xyzw, n, false);
+    if (rc) return rc;
+    h->aligned = false;
+  } else if (!s.src.valid) {
+    return fail(h, B2ICP_ERR_NO_SOURCE, "no scan retained: pass the cloud or call b2icp_mapper_register first");
+  }
+  const size_t m = s.src.n;
+  CK(h->xf_out.ensure(m * sizeof(float4)));
+  CK(h->mat.ensure(32 * sizeof(float)));
+  CK(cudaMemcpyAsync(h->mat.p, T, 16 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+  // lines 157-158: cloud_in_map = refined_pose (x) cloud; addPointsToMap(cloud_in_map)
+  transform_cloud_f<<<(unsigned)((m + 255) / 256), 256, 0, h->stream>>>(s.src.raw.as<float4>(), (int)m, h->mat.as<float>(),
+                                                                      h->xf_out.as<float4>());
+  h->launches += 1;
+  return map_insert_impl(h, h->xf_out.as<float>(), m, true, n_added);
+}
+
 int b2icp_set_target_map(b2icp_handle* h) {
   if (!h) return B2ICP_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lk(h->mu);

@@ -94,7 +94,7 @@ EXPORTS = [
     "b2icp_set_stream", "b2icp_compute_covariances", "b2icp_voxel_filter", "b2icp_get_timing",
     "b2icp_align_batch_submit", "b2icp_align_batch_submit_device", "b2icp_align_batch_wait",
     "b2icp_map_reset", "b2icp_map_insert", "b2icp_map_insert_device", "b2icp_map_size", "b2icp_map_download",
-    "b2icp_map_nearest", "b2icp_set_target_map",
+    "b2icp_map_nearest", "b2icp_set_target_map", "b2icp_mapper_register", "b2icp_mapper_grow",
     "b2icp_get_grid_info", "b2icp_host_alloc", "b2icp_host_free", "b2icp_last_error", "b2icp_status_string",
     "b2icp_version",
 ]
@@ -147,6 +147,8 @@ def load_library() -> C.CDLL:
     L.b2icp_map_download.argtypes = [vp, vp, C.c_size_t, szp]
     L.b2icp_map_nearest.argtypes = [vp, vp, C.c_size_t, vp, vp, szp]
     L.b2icp_set_target_map.argtypes = [vp]
+    L.b2icp_mapper_register.argtypes = [vp, vp, C.c_size_t, vp, vp, C.POINTER(Result)]
+    L.b2icp_mapper_grow.argtypes = [vp, vp, C.c_size_t, vp, szp]
     L.b2icp_get_timing.argtypes = [vp, C.POINTER(Timing)]
     L.b2icp_get_grid_info.argtypes = [vp, fp, ip, dp]
     L.b2icp_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
@@ -451,6 +453,28 @@ class Registration:
         n_nn = C.c_size_t()
         self._check(self._L.b2icp_map_nearest(self._h, _ptr(c), len(c), _ptr(idx), _ptr(nn), C.byref(n_nn)), "map_nearest")
         return idx, nn[: n_nn.value].copy()
+
+    def mapperRegister(self, cloud, T_raw, T_raw_inv):
+        """b2icp_mapper_register: the registration half of OctreeMapper::refineTransformAndGrowMap, device-resident."""
+        c = _cloud(cloud)
+        a = np.ascontiguousarray(T_raw, np.float32)
+        b = np.ascontiguousarray(T_raw_inv, np.float32)
+        rc = self._L.b2icp_mapper_register(self._h, _ptr(c), len(c), _ptr(a), _ptr(b), C.byref(self._result))
+        self._n_source = len(c)
+        self._check(rc, "mapper_register")
+        return self._result
+
+    def mapperGrow(self, T, cloud=None) -> int:
+        """b2icp_mapper_grow: transform the retained (or given) scan by T and add it to the map."""
+        t = np.ascontiguousarray(T, np.float32)
+        n_added = C.c_size_t()
+        if cloud is None:
+            rc = self._L.b2icp_mapper_grow(self._h, None, 0, _ptr(t), C.byref(n_added))
+        else:
+            c = _cloud(cloud)
+            rc = self._L.b2icp_mapper_grow(self._h, _ptr(c), len(c), _ptr(t), C.byref(n_added))
+        self._check(rc, "mapper_grow")
+        return n_added.value
 
     def setInputTargetFromMap(self):
         """The map becomes the registration target without leaving the device."""

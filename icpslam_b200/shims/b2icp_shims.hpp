@@ -337,21 +337,31 @@ class OctreeMapper {
     return false;
   }
   void publishPath(const Pose6DOF&) {}
-  // octree_mapper.cpp:133-173
+  // octree_mapper.cpp:133-173.  The scan is uploaded once (b2icp_mapper_register) and every intermediate cloud
+  // (cloud_in_map, nn_cloud_in_map, nn_cloud) stays on the device; only the 4x4 comes back.  The step-by-step
+  // members above remain for callers that want the intermediate clouds.
   bool refineTransformAndGrowMap(double stamp, const Cloud::Ptr& cloud, const Pose6DOF& raw_pose, Pose6DOF& transform) {
-    Cloud::Ptr cloud_in_map(new Cloud());
-    transformCloudToPoseFrame(cloud, raw_pose, cloud_in_map);
-    if (mapSize() == 0) {
-      addPointsToMap(cloud_in_map);
+    float Tr[16], Tri[16];
+    raw_pose.toMatrix4f(Tr);
+    b2icp_handle* h = search_.get();
+    if (mapSize() == 0) {  // lines 138-142: the first scan seeds the map
+      size_t added = 0;
+      last_status = b2icp_mapper_grow(h, cloud->data(), cloud->size(), Tr, &added);
+      if (added) map_cloud_stale_ = true;
       return false;
     }
-    Cloud::Ptr nn_cloud_in_map(new Cloud()), nn_cloud(new Cloud());
-    approxNearestNeighbors(cloud_in_map, nn_cloud_in_map);
-    transformCloudToPoseFrame(nn_cloud_in_map, raw_pose.inverse(), nn_cloud);
-    if (estimateTransformICP(cloud, nn_cloud, transform, stamp)) {
+    raw_pose.inverse().toMatrix4f(Tri);
+    b2icp_result res;
+    last_status = b2icp_mapper_register(h, cloud->data(), cloud->size(), Tr, Tri, &res);
+    last_result = res;
+    if (last_status == B2ICP_OK && res.converged) {
+      transform = Pose6DOF(res.T, stamp);
       Pose6DOF refined_pose = raw_pose + transform;
-      transformCloudToPoseFrame(cloud, refined_pose, cloud_in_map);
-      addPointsToMap(cloud_in_map);
+      float Tf[16];
+      refined_pose.toMatrix4f(Tf);
+      size_t added = 0;
+      last_status = b2icp_mapper_grow(h, nullptr, 0, Tf, &added);  // the scan is still on the device
+      if (added) map_cloud_stale_ = true;
       return true;
     }
     return false;

@@ -229,6 +229,18 @@ int b2icp_map_size(b2icp_handle* h, size_t* n);
 int b2icp_map_download(b2icp_handle* h, float* out_xyzw, size_t capacity, size_t* n);
 int b2icp_map_nearest(b2icp_handle* h, const float* q_xyzw, size_t n, int32_t* idx, float* nn_xyzw, size_t* n_nn);
 int b2icp_set_target_map(b2icp_handle* h);
+/* OctreeMapper::refineTransformAndGrowMap (octree_mapper.cpp:133-173) with ONE upload of the scan and no cloud coming
+ * back: every intermediate cloud stays in device memory.
+ *   b2icp_mapper_register  cloud_in_map = T_raw * cloud (line 136); nn_cloud_in_map = the map point nearest to every
+ *                          scan point (line 145); nn_cloud = T_raw_inv * nn_cloud_in_map (line 149);
+ *                          estimateTransformICP(cloud, nn_cloud) (line 152) -> *out.  T_raw / T_raw_inv: row-major
+ *                          float 4x4 of raw_pose and its inverse (what pcl_ros::transformPointCloud builds from the
+ *                          tf::Transform).  B2ICP_ERR_NO_TARGET while the map is empty (the caller then only grows).
+ *   b2icp_mapper_grow      cloud_in_map = T * cloud; addPointsToMap(cloud_in_map) (lines 139-140, 157-158).  xyzw == NULL:
+ *                          the scan of the last b2icp_mapper_register call, still on the device. */
+int b2icp_mapper_register(b2icp_handle* h, const float* xyzw, size_t n, const float* T_raw, const float* T_raw_inv,
+                          b2icp_result* out);
+int b2icp_mapper_grow(b2icp_handle* h, const float* xyzw, size_t n, const float* T, size_t* n_added);
 
 int b2icp_get_timing(b2icp_handle* h, b2icp_timing* out);
 /* Neighbour grid of the current target (the structure that replaces the FLANN k-d tree): cell edge,

@@ -570,3 +570,34 @@ def test_map_nearest_matches_oracle_and_feeds_icp(R, oracle):
     reg2.setInputSource(sw[2])
     reg2.align()
     assert np.array_equal(T_map, reg2.getFinalTransformation())
+
+
+@pytest.mark.gpu
+def test_device_resident_mapper_refine_equals_the_step_by_step_path(R, oracle):
+    """b2icp_mapper_register / _grow (scan uploaded once, every intermediate cloud on the device) against the same
+    sequence made of the separate calls the reference's refineTransformAndGrowMap makes (octree_mapper.cpp:133-173)."""
+    from icpslam_b200 import pose6dof
+    _, poses, sw = synth.sweep_sequence(12, 4, n_beams=64, n_az=256)
+    fused = R.Registration(preset=R.PRESET_MAPPER)
+    steps = R.Registration(preset=R.PRESET_MAPPER)
+    icp = R.Registration(preset=R.PRESET_MAPPER)
+    fused.resetMap(0.2)
+    steps.resetMap(0.2)
+    T0 = poses[0].astype(np.float32)
+    assert fused.mapperGrow(T0, sw[0]) == steps.addPointsToMap(steps.transformPointCloud(sw[0], T0, double=False))
+    for k in (1, 2, 3):
+        Tr = poses[k - 1].astype(np.float32)                 # the odometry guess: the previous pose
+        Tri = np.linalg.inv(poses[k - 1]).astype(np.float32)
+        res = fused.mapperRegister(sw[k], Tr, Tri)
+        cloud_in_map = steps.transformPointCloud(sw[k], Tr, double=False)
+        _, nn_in_map = steps.approxNearestNeighbors(cloud_in_map)
+        nn_cloud = steps.transformPointCloud(nn_in_map, Tri, double=False)
+        icp.setInputSource(sw[k])
+        icp.setInputTarget(nn_cloud)
+        icp.align()
+        assert np.array_equal(res.matrix(), icp.getFinalTransformation()) and res.iterations == icp.iterations
+        o = oracle.align(oracle.default_params("mapper"), sw[k], nn_cloud)
+        assert_transform_close(res.matrix(), o["T"])
+        Tf = (poses[k - 1] @ res.matrix()).astype(np.float32)
+        assert fused.mapperGrow(Tf) == steps.addPointsToMap(steps.transformPointCloud(sw[k], Tf, double=False))
+    assert np.array_equal(fused.mapCloud(), steps.mapCloud())
