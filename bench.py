@@ -450,6 +450,25 @@ def main():
                 # cached-neighbour certificate (icpslam_b200/csrc/nncache.cuh)
                 "searched_fraction": float(np.sum(searches)) / max(1.0, float(sum(sum(x) for x in iters_hist)) * N_SWEEP)}
 
+    # ---- the stand-alone NN search (b2icp_nn_search_device): the second half of BASELINE.json's metric ----
+    # all 32 sweeps of the step as ONE query cloud (2.1 M queries) against the 500k map, exact unbounded 1-NN,
+    # no seeds: algorithmic bytes = 16 n_q + 16 N_t' + 8 n_q, CUDA events inside the library.
+    allq = torch.cat(d_sweeps)
+    nq = allq.shape[0]
+    d_idx = torch.empty(nq, dtype=torch.int32, device=dev)
+    d_d2 = torch.empty(nq, dtype=torch.float32, device=dev)
+    nn_ms = []
+    for k in range(3 + 5):
+        flush.zero_()
+        reg.nearestKSearch1Device(allq.data_ptr(), nq, d_idx.data_ptr(), d_d2.data_ptr())
+        if k >= 3:
+            nn_ms.append(reg.timing().nn_sweep_ms)
+    nn_bytes = 24.0 * nq + 16.0 * nt_touched
+    nn_search = {"kernel": "nn_search_box_kernel (+ nn_brute_fallback)", "queries": int(nq), "ms": float(np.mean(nn_ms)),
+                 "algorithmic_bytes": nn_bytes, "achieved": nn_bytes / (float(np.mean(nn_ms)) * 1e-3) / 1e9, "unit": "GB/s",
+                 "frac": nn_bytes / (float(np.mean(nn_ms)) * 1e-3) / 1e9 / peak,
+                 "queries_per_s": nq / (float(np.mean(nn_ms)) * 1e-3)}
+
     # ---- CPU baseline on this box's host cores (bounded sample) -----------------------------------
     cpu = None
     if world == 1 and args.cpu_sample > 0:
@@ -475,6 +494,7 @@ def main():
                 "d2h_bytes_per_step": Bn * STATE_BYTES, "ms_per_step": 1e3 * e2e_dev_s / args.steps, "api": e2e_api},
         "gpu_launches": int(launches1 - launches0),
         "roofline": roofline,
+        "nn_search": nn_search,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)

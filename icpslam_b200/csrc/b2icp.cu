@@ -122,7 +122,7 @@ struct b2icp_handle {
 
   std::vector<std::unique_ptr<ScanSlot>> slots;
   std::vector<std::unique_ptr<GridSlot>> grids;
-  DeviceBuf states, tasks, unres_list, unres_count;
+  DeviceBuf states, tasks, unres_list, unres_count, unres_keys;
   // K9: the mapper's point map (map.cuh)
   DeviceBuf map_pts, map_keys, map_vals, map_slot_of, map_flags, map_tiles, map_stats;
   size_t map_size = 0, map_table_cap = 0;
@@ -524,6 +524,8 @@ const char* status_message(int s) {
   }
 }
 
+int launch_brute_fallback(b2icp_handle* h, const GridView& view, const float4* d_q, size_t n, int* d_idx, float* d_d2);
+
 // Enqueue getFitnessScore for slot i (result lands in states[i].fitness_*).
 int enqueue_fitness(b2icp_handle* h, int i, double max_range) {
   ScanSlot& s = slot(h, i);
@@ -538,9 +540,10 @@ int enqueue_fitness(b2icp_handle* h, int i, double max_range) {
   fitness_kernel<<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>() + i, kUnboundedRings,
                                                         h->unres_list.as<int>(), h->unres_count.as<unsigned int>(),
                                                         h->query.as<float4>(), h->q_idx.as<int>(), h->q_d2.as<float>());
-  nn_brute_fallback<<<148 * 2, 256, 0, h->stream>>>(g.view, h->query.as<float4>(), h->unres_list.as<int>(),
-                                                    h->unres_count.as<unsigned int>(), h->q_idx.as<int>(),
-                                                    h->q_d2.as<float>());
+  {
+    int rc = launch_brute_fallback(h, g.view, h->query.as<float4>(), n, h->q_idx.as<int>(), h->q_d2.as<float>());
+    if (rc) return rc;
+  }
   fitness_reduce<<<1, 1024, 0, h->stream>>>(h->q_idx.as<int>(), h->q_d2.as<float>(), (int)n, max_range,
                                             h->states.as<IcpState>() + i);
   h->launches += 4;
@@ -551,17 +554,27 @@ double fitness_value(const IcpState& s) {
   return s.fitness_cnt > 0 ? s.fitness_sum / (double)s.fitness_cnt : DBL_MAX;
 }
 
+// exhaustive scan of the queries listed in unres_list (nn.cuh): keys reset, scan, unpack
+int launch_brute_fallback(b2icp_handle* h, const GridView& view, const float4* d_q, size_t n, int* d_idx, float* d_d2) {
+  CK(h->unres_keys.ensure(n * sizeof(unsigned long long)));
+  CK(cudaMemsetAsync(h->unres_keys.p, 0xFF, n * sizeof(unsigned long long), h->stream));
+  nn_brute_fallback<<<dim3(148 * 2, 8, 1), 256, 0, h->stream>>>(view, d_q, h->unres_list.as<int>(),
+                                                             h->unres_count.as<unsigned int>(),
+                                                             h->unres_keys.as<unsigned long long>());
+  nn_brute_unpack<<<148, 256, 0, h->stream>>>(h->unres_list.as<int>(), h->unres_count.as<unsigned int>(),
+                                              h->unres_keys.as<unsigned long long>(), d_idx, d_d2);
+  h->launches += 2;
+  return B2ICP_OK;
+}
+
 int nn_search_impl(b2icp_handle* h, const float4* d_q, size_t n, int* d_idx, float* d_d2, int grid_index = 0) {
   GridSlot& g = gslot(h, (size_t)grid_index);
   CK(h->unres_list.ensure(n * sizeof(int)));
   zero_counter<<<1, 1, 0, h->stream>>>(h->unres_count.as<unsigned int>());
-  nn_search_kernel<<<(unsigned)((n + kSweepThreads - 1) / kSweepThreads), kSweepThreads, 0, h->stream>>>(
-      g.view, d_q, (int)n, INFINITY, kUnboundedRings, d_idx, d_d2, h->unres_list.as<int>(),
-      h->unres_count.as<unsigned int>());
-  nn_brute_fallback<<<148 * 2, 256, 0, h->stream>>>(g.view, d_q, h->unres_list.as<int>(),
-                                                    h->unres_count.as<unsigned int>(), d_idx, d_d2);
-  h->launches += 3;
-  return B2ICP_OK;
+  nn_search_box_kernel<<<(unsigned)((n + kSweepThreads - 1) / kSweepThreads), kSweepThreads, 0, h->stream>>>(
+      g.view, d_q, (int)n, kUnboundedRings, d_idx, d_d2, h->unres_list.as<int>(), h->unres_count.as<unsigned int>());
+  h->launches += 2;
+  return launch_brute_fallback(h, g.view, d_q, n, d_idx, d_d2);
 }
 
 #include "gicp_host.inl"
@@ -798,7 +811,7 @@ int b2icp_destroy(b2icp_handle* h) {
   for (auto& g : h->grids) g->release();
   for (DeviceBuf* b : {&h->map_pts, &h->map_keys, &h->map_vals, &h->map_slot_of, &h->map_flags, &h->map_tiles, &h->map_stats})
     b->release();
-  for (DeviceBuf* b : {&h->states, &h->tasks, &h->unres_list, &h->unres_count, &h->query, &h->q_idx, &h->q_d2, &h->xf_in,
+  for (DeviceBuf* b : {&h->states, &h->tasks, &h->unres_list, &h->unres_count, &h->unres_keys, &h->query, &h->q_idx, &h->q_d2, &h->xf_in,
                        &h->xf_out, &h->mat})
     b->release();
   for (cudaEvent_t e : h->events) cudaEventDestroy(e);

@@ -221,6 +221,47 @@ __device__ __forceinline__ void box_search(const GridView& g, float qx, float qy
   }
 }
 
+// ---- stand-alone exact 1-NN (b2icp_nn_search, K9's map_nearest): probe, then one box scan -------------------
+// The probe (own cell, then the 3x3x3 block) gives a radius that contains the nearest neighbour; the box of that
+// radius is scanned once.  The answer is exact iff the best candidate is closer than everything outside the scanned
+// box (`lrest`); otherwise (nothing within `max_span` cells) the query goes to the exhaustive fallback of nn.cuh.
+// Algorithmic bytes per launch: 16 n_q (queries) + 16 N_t' (each target point in a touched cell once) + 8 n_q.
+__global__ void __launch_bounds__(kSweepThreads) nn_search_box_kernel(GridView g, const float4* __restrict__ q, int n,
+                                                                      int max_span, int* __restrict__ idx,
+                                                                      float* __restrict__ d2,
+                                                                      int* __restrict__ unresolved_list,
+                                                                      unsigned int* __restrict__ unresolved_count) {
+  __shared__ NNScratch<kSweepThreads> sc;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = __ldg(q + i);
+  if (!(isfinite(p.x) && isfinite(p.y) && isfinite(p.z))) {
+    idx[i] = -1;
+    d2[i] = INFINITY;
+    return;
+  }
+  const float seed = probe_seed(g, p.x, p.y, p.z);
+  Top3 top;
+  float lrest, best;
+  bool exact = false;
+  // queries with nothing nearby widen the box once (3 -> 10 cells either side) before giving up: the exhaustive
+  // scan reads the whole target per query and is worth avoiding for the sparse fringe of a map
+  for (int span = max_span; !exact && span <= 3 * max_span + 1; span = 3 * span + 1) {
+    const CellBox bx = cell_box(g, p.x, p.y, p.z, seed, INFINITY, 0.01f * g.cell, span);
+    box_search<kSweepThreads>(g, p.x, p.y, p.z, bx, sc, top, lrest);
+    best = key_d2(top.k0);
+    exact = top.k0 != kInfKey && (!(lrest < INFINITY) || best < __fmul_rd(__fmul_rd(lrest, lrest), kRelDown));
+    if (seed < INFINITY) break;  // the probe's radius already contains the answer: one pass is exact
+  }
+  if (!exact) {
+    const unsigned int slot = atomicAdd(unresolved_count, 1u);
+    unresolved_list[slot] = i;
+    return;
+  }
+  idx[i] = key_idx(top.k0);
+  d2[i] = best;
+}
+
 // lower bound on the distance to every target point other than top.p0 / top.p1
 __device__ __forceinline__ float top3_bound(const Top3& top, float lrest) {
   const float l3 = top.b2 < INFINITY ? __fmul_rd(sqrt_fast(top.b2), kRelDown) : INFINITY;
