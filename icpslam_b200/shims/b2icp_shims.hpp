@@ -13,11 +13,12 @@
 // row-major.  ROS publishers / subscribers / TF are out of scope; the methods that only did that are
 // kept as no-ops so call sites compile unchanged.
 //
-// Every registration, transform and search below is a call of the C ABI: there is no CPU path.  The
-// two map operations that the reference delegates to pcl::octree (addPointsToMap's one-point-per-voxel
-// rule, approxNearestNeighbors) are SURVEY.md §8f "next" rows: the map's dedup set (pure bookkeeping, no
-// arithmetic) lives on the host here, and neighbours come from the engine's EXACT search (documented deviation from PCL's greedy
-// approxNearestSearch: never farther than PCL's answer).
+// Every registration, transform, filter, map operation and search below is a call of the C ABI: there is no CPU
+// path.  The map of OctreeMapper (pcl::octree in the reference) lives in device memory behind b2icp_map_*
+// (csrc/map.cuh): one point per voxel, first come wins, scan order kept; neighbours come from the engine's EXACT
+// search (documented deviation from PCL's greedy approxNearestSearch: never farther than PCL's answer), and
+// refineTransformAndGrowMap uploads the scan once and keeps every intermediate cloud on the device
+// (b2icp_mapper_register / b2icp_mapper_grow).
 #pragma once
 #include <cmath>
 #include <cstdint>
@@ -27,7 +28,6 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
-#include <unordered_set>
 #include <vector>
 
 #include "../../include/b2icp.h"
