@@ -215,7 +215,9 @@ def workload_config(batch: int, world: int, extra=None) -> dict:
         "sweep_points": N_SWEEP, "map_points": N_MAP, "max_iterations": MAX_ITERS, "transformation_epsilon": 1e-6,
         "max_correspondence_distance": 1.0, "batch_per_gpu": batch, "global_batch": batch * world,
         "sharding": "scans sharded across ranks, map replicated; NCCL all_gather of per-scan transforms per step",
-        "l2": "flushed between timed steps (256 MiB write)",
+        "l2": "a 256 MiB write is enqueued between step submissions (in the streamed legs it runs next to the batches in "
+              "flight); independently of it the per-step working set (150 MB of per-query state per 32-sweep step, up to "
+              "8 steps in flight) is larger than the 126 MB L2",
     }
     if extra:
         c.update(extra)
