@@ -44,6 +44,7 @@ constexpr int kUnboundedRings = 3;        // ring budget of unbounded searches b
 constexpr double kTargetOccupancy = 2.5;  // points per occupied cell the auto-sizing aims at
 constexpr double kMaxOccupancy = 4.0;     // above this the grid is rebuilt with smaller cells
 constexpr float kCacheMarginFrac = 0.05f;  // nncache.cuh: box-search margin as a fraction of the cell edge
+constexpr int kStreamedQpt = 16;          // slab length of streamed batches (4: 15.5k, 8: 18.6k, 16: 20.7k scans/s)
 constexpr int kFirstSweepQpt = 2;         // slab length (x 32 queries per warp) of the first sweep of a batch
 constexpr int kMaxBatch = 64;             // scans advanced together by one sweep launch
 constexpr int kStreamSets = 8;            // streamed batches in flight (b2icp_align_batch_submit / _wait)
@@ -393,7 +394,7 @@ void fill_result(const IcpState& s, b2icp_result* out) {
 
 // Advance slots [0, B) to convergence: one fused sweep launch per iteration for the whole batch.
 // guesses: B x 16 floats or NULL.  Results are read back by read_states().
-int run_batch(b2icp_handle* h, int B, const float* guesses, int slot0 = 0, bool allow_prof = true) {
+int run_batch(b2icp_handle* h, int B, const float* guesses, int slot0 = 0, bool allow_prof = true, bool streamed = false) {
   if (h->params.mode != B2ICP_MODE_P2P_SVD) return fail(h, B2ICP_ERR_INVALID_ARG, "mode not implemented");
   size_t max_n = 0;
   double min_cell = 1e300;
@@ -447,21 +448,27 @@ int run_batch(b2icp_handle* h, int B, const float* guesses, int slot0 = 0, bool 
   // (measured on B200, 32 x 64k sweeps: qpt 2 -> 144 us, 4 -> 113 us, 8 -> 109 us per iteration)
   auto ctas_at = [&](int qpt) { return (long long)B * (long long)((max_n + (size_t)kSweepThreads * qpt - 1) / ((size_t)kSweepThreads * qpt)); };
   const long long want = 2LL * 148 * kSweepMinCtas;
-  const int qpt = h->qpt_override > 0 ? h->qpt_override
-                                      : (ctas_at(8) >= want ? 8 : (ctas_at(4) >= want ? 4 : (ctas_at(2) >= want ? 2 : 1)));
+  int qpt = h->qpt_override > 0 ? h->qpt_override
+                                : (ctas_at(8) >= want ? 8 : (ctas_at(4) >= want ? 4 : (ctas_at(2) >= want ? 2 : 1)));
+  if (streamed && h->qpt_override <= 0 && ctas_at(16) >= want / 2) qpt = kStreamedQpt;
   // The slab length can change from one launch to the next (the work list lives inside a launch).  The first
   // sweeps search most queries, so their warps are long-running whatever the slab: shorter slabs there keep
   // the last wave of CTAs from running on a third of the machine.
   auto qpt_at = [&](int it) {
     if (!h->qpt_sched.empty()) return h->qpt_sched[std::min<size_t>((size_t)it, h->qpt_sched.size() - 1)];
     // measured on B200 (32 x 64k sweeps, scans/s): 8 everywhere 10 144; 2,8.. 10 451; 2,4,4,8.. 10 533; 2,4,4,4,4,8.. 10 571
+    // A streamed batch shares the device with the other batches in flight, which fill its tails: long slabs
+    // everywhere are best there (18.6k scans/s against 17.2k with the schedule below).
+    if (streamed) return qpt;
     return it == 0 ? std::min(qpt, kFirstSweepQpt) : (it <= 4 ? std::min(qpt, 4) : qpt);
   };
   for (int it = 0; it < iters; ++it) {
     if (prof) CK(cudaEventRecord(h->events[2 + 2 * it], h->stream));
     const int q = qpt_at(it);
     const dim3 grid((unsigned)((max_n + (size_t)kSweepThreads * q - 1) / ((size_t)kSweepThreads * q)), (unsigned)B, 1);
-    if (q == 8)
+    if (q == 16)
+      icp_sweep_p2p<16><<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
+    else if (q == 8)
       icp_sweep_p2p<8><<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
     else if (q == 4)
       icp_sweep_p2p<4><<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
@@ -773,7 +780,7 @@ int b2icp_create(const b2icp_params* p, b2icp_handle** out) {
   if (const char* e = getenv("B2ICP_QPT_SCHED"))
     for (const char* p = e; *p;) {
       const int v = atoi(p);
-      h->qpt_sched.push_back(v >= 8 ? 8 : (v >= 4 ? 4 : (v >= 2 ? 2 : 1)));
+      h->qpt_sched.push_back(v >= 16 ? 16 : (v >= 8 ? 8 : (v >= 4 ? 4 : (v >= 2 ? 2 : 1))));
       while (*p && *p != ',') ++p;
       if (*p == ',') ++p;
     }
@@ -1122,7 +1129,7 @@ static int submit_impl(b2icp_handle* h, const float* const* src, const size_t* n
     for (int k = 0; k < h->n_pending; ++k) CK(cudaStreamWaitEvent(cs, h->set_done[h->pending[(h->first_pending + k) % kStreamSets].set], 0));
   CK(cudaStreamWaitEvent(cs, h->set_uploaded[set], 0));
   h->stream = cs;
-  int rc = run_batch(h, B, nullptr, slot0, false);
+  int rc = run_batch(h, B, nullptr, slot0, false, true);
   if (!rc && with_fitness)
     for (int i = 0; i < B && !rc; ++i) rc = enqueue_fitness(h, slot0 + i, DBL_MAX);
   h->stream = saved;
