@@ -44,7 +44,7 @@ constexpr int kUnboundedRings = 3;        // ring budget of unbounded searches b
 constexpr double kTargetOccupancy = 2.5;  // points per occupied cell the auto-sizing aims at
 constexpr double kMaxOccupancy = 4.0;     // above this the grid is rebuilt with smaller cells
 constexpr float kCacheMarginFrac = 0.05f;  // nncache.cuh: box-search margin as a fraction of the cell edge
-constexpr int kStreamedQpt = 16;          // slab length of streamed batches (4: 15.5k, 8: 18.6k, 16: 20.7k scans/s)
+constexpr int kStreamedQpt = 32;          // slab length of streamed batches (4: 15.5k, 8: 18.6k, 16: 21.7k, 32: 23.2k scans/s)
 constexpr int kFirstSweepQpt = 2;         // slab length (x 32 queries per warp) of the first sweep of a batch
 constexpr int kMaxBatch = 64;             // scans advanced together by one sweep launch
 constexpr int kStreamSets = 8;            // streamed batches in flight (b2icp_align_batch_submit / _wait)
@@ -450,7 +450,7 @@ int run_batch(b2icp_handle* h, int B, const float* guesses, int slot0 = 0, bool 
   const long long want = 2LL * 148 * kSweepMinCtas;
   int qpt = h->qpt_override > 0 ? h->qpt_override
                                 : (ctas_at(8) >= want ? 8 : (ctas_at(4) >= want ? 4 : (ctas_at(2) >= want ? 2 : 1)));
-  if (streamed && h->qpt_override <= 0 && ctas_at(16) >= want / 2) qpt = kStreamedQpt;
+  if (streamed && h->qpt_override <= 0 && ctas_at(kStreamedQpt) >= 128) qpt = kStreamedQpt;
   // The slab length can change from one launch to the next (the work list lives inside a launch).  The first
   // sweeps search most queries, so their warps are long-running whatever the slab: shorter slabs there keep
   // the last wave of CTAs from running on a third of the machine.
@@ -466,7 +466,9 @@ int run_batch(b2icp_handle* h, int B, const float* guesses, int slot0 = 0, bool 
     if (prof) CK(cudaEventRecord(h->events[2 + 2 * it], h->stream));
     const int q = qpt_at(it);
     const dim3 grid((unsigned)((max_n + (size_t)kSweepThreads * q - 1) / ((size_t)kSweepThreads * q)), (unsigned)B, 1);
-    if (q == 16)
+    if (q == 32)
+      icp_sweep_p2p<32><<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
+    else if (q == 16)
       icp_sweep_p2p<16><<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
     else if (q == 8)
       icp_sweep_p2p<8><<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
@@ -780,7 +782,7 @@ int b2icp_create(const b2icp_params* p, b2icp_handle** out) {
   if (const char* e = getenv("B2ICP_QPT_SCHED"))
     for (const char* p = e; *p;) {
       const int v = atoi(p);
-      h->qpt_sched.push_back(v >= 16 ? 16 : (v >= 8 ? 8 : (v >= 4 ? 4 : (v >= 2 ? 2 : 1))));
+      h->qpt_sched.push_back(v >= 32 ? 32 : v >= 16 ? 16 : (v >= 8 ? 8 : (v >= 4 ? 4 : (v >= 2 ? 2 : 1))));
       while (*p && *p != ',') ++p;
       if (*p == ',') ++p;
     }

@@ -58,7 +58,6 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) icp_sweep_p2p(co
   __shared__ NNScratch<kSweepThreads> sc;             // one column per thread: private to its warp by construction
   __shared__ float sT[kWarps][16];
   __shared__ unsigned short wl_id[kWarps][kWarpSlab];  // work list of the warp: query index inside its slab
-  __shared__ float wl_thr[kWarps][kWarpSlab];          // squared distance of the best cached candidate (+inf: none)
   const ScanTask& t = tasks[blockIdx.y];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nslab = (t.n + kWarpSlab - 1) / kWarpSlab;
@@ -83,7 +82,6 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) icp_sweep_p2p(co
   for (int qi = 0; qi < QPT; ++qi) {
     const int i = base + qi * 32 + lane;
     bool need = false;
-    float seed = INFINITY;
     if (i < t.n) {
       float4 p, c0, c1;
       float lb = 0.0f;
@@ -124,16 +122,11 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) icp_sweep_p2p(co
           if ((d2 < L2) && !((double)d2 > cfg.max2)) accumulate_pair(acc, q, c0, d2);
         } else {
           need = true;
-          seed = d2;
         }
       }
     }
     const unsigned bal = __ballot_sync(0xFFFFFFFFu, need);
-    if (need) {
-      const int slot = wc + __popc(bal & ((1u << lane) - 1u));
-      wl_id[warp][slot] = (unsigned short)(qi * 32 + lane);
-      wl_thr[warp][slot] = seed;
-    }
+    if (need) wl_id[warp][wc + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)(qi * 32 + lane);
     wc += __popc(bal);
   }
   __syncwarp();
@@ -142,7 +135,14 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) icp_sweep_p2p(co
   for (int e = lane; e < wc; e += 32) {
     const int i = base + (int)wl_id[warp][e];
     const float4 q = t.cur[i];
-    float seed = wl_thr[warp][e];
+    // search radius: the nearer cached candidate (the list keeps ids only, so that long slabs fit in shared
+    // memory; the two points are L2-hot), or the probe when there is none
+    float seed = INFINITY;
+    if (!first) {
+      const float4 c0 = t.c0[i], c1 = t.c1[i];
+      if (__float_as_int(c0.w) >= 0) seed = sqdist3(q.x, q.y, q.z, c0.x, c0.y, c0.z);
+      if (__float_as_int(c1.w) >= 0) seed = fminf(seed, sqdist3(q.x, q.y, q.z, c1.x, c1.y, c1.z));
+    }
     if (!(seed < INFINITY)) seed = probe_seed(t.grid, q.x, q.y, q.z);
     const CellBox bx = cell_box(t.grid, q.x, q.y, q.z, seed, cfg.bound2, margin, cfg.max_rings);
     Top3 top;
