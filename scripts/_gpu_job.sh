@@ -1,5 +1,4 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-for v in "B2ICP_X=1" "B2ICP_QPT_SCHED=32" "B2ICP_QPT_SCHED=8"; do
+for v in "B2ICP_X=1" "B2ICP_QPT_SCHED=64"; do
 echo "== $v"
 env $v python bench.py --steps 16 --warmup 8 --cpu-sample 0 2>/dev/null | python -c "
 import json,sys
