@@ -233,28 +233,8 @@ __device__ __forceinline__ NNResult grid_nn(const GridView& g, float qx, float q
   return r;
 }
 
-// ---- stand-alone NN sweep (b2icp_nn_search): the roofline kernel ------------------------------
-// Algorithmic bytes per launch: 16 n_q (queries) + 16 N_t' (each target point in a touched cell once)
-// + 8 n_q (idx + d2).
-__global__ void __launch_bounds__(kSweepThreads) nn_search_kernel(GridView g, const float4* __restrict__ q, int n,
-                                                                  float bound2, int max_rings,
-                                                                  int* __restrict__ idx, float* __restrict__ d2,
-                                                                  int* __restrict__ unresolved_list,
-                                                                  unsigned int* __restrict__ unresolved_count) {
-  __shared__ NNScratch<kSweepThreads> sc;
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float4 p = __ldg(q + i);
-  NNResult r = grid_nn<kSweepThreads>(g, p.x, p.y, p.z, bound2, max_rings, -1, sc);
-  if (!r.resolved) {
-    unsigned int slot = atomicAdd(unresolved_count, 1u);
-    unresolved_list[slot] = i;
-    return;
-  }
-  int id = key_idx(r.key);
-  idx[i] = (r.key == kInfKey) ? -1 : id;
-  d2[i] = key_d2(r.key);
-}
+// (The stand-alone search entry point, nn_search_box_kernel, lives in nncache.cuh; grid_nn above serves
+// getFitnessScore's uncertified queries and GICP's correspondence kernel, which need seeds by position.)
 
 // Fallback for the queries whose ring budget ran out (far outside the map): exhaustive scan.  CTA x owns one
 // chunk of the sorted target array (it stays in L1 while the CTA walks the list of queries, blockIdx.y-strided),
