@@ -78,6 +78,7 @@ struct ScanTask {
   int* corr_pos;       // [n] sorted-array position of the last match (seed of the next search), -1 = none
   float4* c0;          // [n] nearest target point found for cur[i]: xyz + original index (int bits, -1 = none)
   float4* c1;          // [n] runner-up, same layout (nncache.cuh)
+  float4* c2;          // [n] third nearest (used when kCacheK == 3)
   float* lb;           // [n] lower bound on the distance from cur[i] to every target point other than c0, c1
   double* partials;    // [ceil(n / 32)][kNumSums] per-warp sums of one sweep
   IcpState* state;

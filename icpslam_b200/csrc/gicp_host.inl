@@ -598,6 +598,7 @@ int run_gicp(b2icp_handle* h, const float* guess16) {
   t.corr_pos = s.corr_pos.as<int>();
   t.c0 = s.c0.as<float4>();
   t.c1 = s.c1.as<float4>();
+  t.c2 = s.c2.as<float4>();
   t.lb = s.lb.as<float>();
   t.partials = s.partials.as<double>();
   t.state = h->states.as<IcpState>();

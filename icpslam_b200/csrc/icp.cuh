@@ -72,6 +72,8 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) icp_sweep_p2p(co
   const int base = slab * kWarpSlab;
   const float margin = cfg.margin_frac * t.grid.cell;
 
+  float4* const cand[3] = {t.c0, t.c1, t.c2};  // the first kCacheK are used
+
   double acc[kNumSums];
 #pragma unroll
   for (int c = 0; c < kNumSums; ++c) acc[c] = 0.0;
@@ -83,22 +85,22 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) icp_sweep_p2p(co
     const int i = base + qi * 32 + lane;
     bool need = false;
     if (i < t.n) {
-      float4 p, c0, c1;
+      float4 p, c[kCacheK];
       float lb = 0.0f;
       if (first) {
         p = __ldg(t.src + i);
-      } else {  // four independent coalesced loads
+      } else {  // independent coalesced loads
         p = ld_stream(t.cur + i);
-        c0 = ld_stream(t.c0 + i);
-        c1 = ld_stream(t.c1 + i);
+#pragma unroll
+        for (int k = 0; k < kCacheK; ++k) c[k] = ld_stream(cand[k] + i);
         lb = ld_stream(t.lb + i);
       }
       const float4 q = xform_f(T, p.x, p.y, p.z);
       st_stream(t.cur + i, q);
       if (!(isfinite(q.x) && isfinite(q.y) && isfinite(q.z))) {
         atomicOr(&st->pad, 1);  // non-finite source point or transform: reported by the last warp
-        t.c0[i] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-        t.c1[i] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+#pragma unroll
+        for (int k = 0; k < kCacheK; ++k) cand[k][i] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
         t.lb[i] = 0.0f;
       } else if (first) {
         need = true;
@@ -106,15 +108,25 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) icp_sweep_p2p(co
         // bound after this iteration's motion (upper-rounded step, lower-rounded difference)
         const float step = __fmul_ru(sqrt_fast(sqdist3(q.x, q.y, q.z, p.x, p.y, p.z)), kRelUp);
         const float L = __fsub_rd(lb, step);
-        const int i0 = __float_as_int(c0.w), i1 = __float_as_int(c1.w);
-        unsigned long long k0 = i0 >= 0 ? pack_key(sqdist3(q.x, q.y, q.z, c0.x, c0.y, c0.z), i0) : kInfKey;
-        const unsigned long long k1 = i1 >= 0 ? pack_key(sqdist3(q.x, q.y, q.z, c1.x, c1.y, c1.z), i1) : kInfKey;
-        if (k1 < k0) {  // keep c0 = the nearer of the two
-          k0 = k1;
-          st_stream(t.c0 + i, c1);
-          st_stream(t.c1 + i, c0);
-          c0 = c1;
+        unsigned long long k0 = kInfKey;
+        int arg = 0;
+#pragma unroll
+        for (int k = 0; k < kCacheK; ++k) {
+          const int id = __float_as_int(c[k].w);
+          const unsigned long long kk = id >= 0 ? pack_key(sqdist3(q.x, q.y, q.z, c[k].x, c[k].y, c[k].z), id) : kInfKey;
+          if (kk < k0) {
+            k0 = kk;
+            arg = k;
+          }
         }
+        float4 c0 = c[0];
+#pragma unroll
+        for (int k = 1; k < kCacheK; ++k)
+          if (arg == k) {  // keep c0 = the nearest of the cached points
+            st_stream(cand[0] + i, c[k]);
+            st_stream(cand[k] + i, c[0]);
+            c0 = c[k];
+          }
         const float d2 = key_d2(k0);
         const float L2 = L > 0.0f ? __fmul_rd(__fmul_rd(L, L), kRelDown) : 0.0f;
         if (fminf(d2, cfg.bound2) < L2) {  // certificate holds: the NN is c0, or nothing is within the bound
@@ -139,9 +151,11 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) icp_sweep_p2p(co
     // memory; the two points are L2-hot), or the probe when there is none
     float seed = INFINITY;
     if (!first) {
-      const float4 c0 = t.c0[i], c1 = t.c1[i];
-      if (__float_as_int(c0.w) >= 0) seed = sqdist3(q.x, q.y, q.z, c0.x, c0.y, c0.z);
-      if (__float_as_int(c1.w) >= 0) seed = fminf(seed, sqdist3(q.x, q.y, q.z, c1.x, c1.y, c1.z));
+#pragma unroll
+      for (int k = 0; k < kCacheK; ++k) {
+        const float4 ck = cand[k][i];
+        if (__float_as_int(ck.w) >= 0) seed = fminf(seed, sqdist3(q.x, q.y, q.z, ck.x, ck.y, ck.z));
+      }
     }
     if (!(seed < INFINITY)) seed = probe_seed(t.grid, q.x, q.y, q.z);
     const CellBox bx = cell_box(t.grid, q.x, q.y, q.z, seed, cfg.bound2, margin, cfg.max_rings);
@@ -149,9 +163,10 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) icp_sweep_p2p(co
     float lrest;
     box_search<kSweepThreads>(t.grid, q.x, q.y, q.z, bx, sc, top, lrest);
     const float4 none = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-    const float4 m0 = top.p0 >= 0 ? __ldg(t.grid.pts + top.p0) : none;
-    st_stream(t.c0 + i, m0);
-    st_stream(t.c1 + i, top.p1 >= 0 ? __ldg(t.grid.pts + top.p1) : none);
+    const float4 m0 = top.p[0] >= 0 ? __ldg(t.grid.pts + top.p[0]) : none;
+    st_stream(cand[0] + i, m0);
+#pragma unroll
+    for (int k = 1; k < kCacheK; ++k) st_stream(cand[k] + i, top.p[k] >= 0 ? __ldg(t.grid.pts + top.p[k]) : none);
     st_stream(t.lb + i, top3_bound(top, lrest));
     const float d2 = key_d2(top.k0);
     if ((top.k0 != kInfKey) && !((double)d2 > cfg.max2)) accumulate_pair(acc, q, m0, d2);
@@ -230,13 +245,17 @@ __global__ void __launch_bounds__(kSweepThreads) fitness_kernel(const ScanTask* 
   if (t.pad) {
     // the point-to-point loop left its certificate (nncache.cuh) for cur[i], which is final_T * src[i] up to
     // the last increment and float rounding: the same triangle-inequality test settles most queries here too
-    const float4 c = t.cur[i], c0 = t.c0[i], c1 = t.c1[i];
+    const float4 c = t.cur[i];
     const float step = __fmul_ru(sqrt_fast(sqdist3(q.x, q.y, q.z, c.x, c.y, c.z)), kRelUp);
     const float L = __fsub_rd(t.lb[i], step);
-    const int i0 = __float_as_int(c0.w), i1 = __float_as_int(c1.w);
-    const unsigned long long k0 = i0 >= 0 ? pack_key(sqdist3(q.x, q.y, q.z, c0.x, c0.y, c0.z), i0) : kInfKey;
-    const unsigned long long k1 = i1 >= 0 ? pack_key(sqdist3(q.x, q.y, q.z, c1.x, c1.y, c1.z), i1) : kInfKey;
-    seed = k1 < k0 ? k1 : k0;
+    const float4* const cand[3] = {t.c0, t.c1, t.c2};
+#pragma unroll
+    for (int k = 0; k < kCacheK; ++k) {
+      const float4 ck = cand[k][i];
+      const int id = __float_as_int(ck.w);
+      const unsigned long long kk = id >= 0 ? pack_key(sqdist3(q.x, q.y, q.z, ck.x, ck.y, ck.z), id) : kInfKey;
+      seed = kk < seed ? kk : seed;
+    }
     const float L2 = L > 0.0f ? __fmul_rd(__fmul_rd(L, L), kRelDown) : 0.0f;
     if (key_d2(seed) < L2) {
       idx_out[i] = key_idx(seed);
