@@ -99,11 +99,11 @@ struct GridSlot {
 
 struct ScanSlot {
   Cloud src;
-  DeviceBuf cur, corr_idx, corr_d2, corr_pos, c0, c1, c2, lb, partials;
+  DeviceBuf cur, corr_idx, corr_d2, corr_pos, c0, c1, c2, partials;
   DeviceBuf cov, mahal, gicp_partials;  // GICP: source covariances, Mahalanobis matrices, per-CTA sums
   int grid = 0;
   void release() {
-    for (DeviceBuf* b : {&src.raw, &cur, &corr_idx, &corr_d2, &corr_pos, &c0, &c1, &c2, &lb, &partials, &cov, &mahal, &gicp_partials})
+    for (DeviceBuf* b : {&src.raw, &cur, &corr_idx, &corr_d2, &corr_pos, &c0, &c1, &c2, &partials, &cov, &mahal, &gicp_partials})
       b->release();
   }
 };
@@ -371,7 +371,6 @@ int ensure_slot_work(b2icp_handle* h, ScanSlot& s) {
   CK(s.c0.ensure(n * sizeof(float4)));
   CK(s.c1.ensure(n * sizeof(float4)));
   if (kCacheK > 2) CK(s.c2.ensure(n * sizeof(float4)));
-  CK(s.lb.ensure(n * sizeof(float)));
   CK(s.partials.ensure(ncta * kNumSums * sizeof(double)));
   return B2ICP_OK;
 }
@@ -416,7 +415,6 @@ int run_batch(b2icp_handle* h, int B, const float* guesses, int slot0 = 0, bool 
     t.c0 = s.c0.as<float4>();
     t.c1 = s.c1.as<float4>();
     t.c2 = s.c2.as<float4>();
-    t.lb = s.lb.as<float>();
     t.partials = s.partials.as<double>();
     t.state = h->states.as<IcpState>() + slot0 + i;
     t.n = (int)s.src.n;

@@ -72,14 +72,14 @@ struct IcpConfig {
 struct ScanTask {
   GridView grid;
   const float4* src;   // source as uploaded (w ignored)
-  float4* cur;         // input_transformed: rewritten in place by every sweep
+  float4* cur;         // input_transformed: rewritten in place by every sweep; .w = lower bound on the distance from
+                       // the point to every target point other than its cached neighbours (nncache.cuh)
   int* corr_idx;       // [n] target index of the last sweep, -1 = gated out
   float* corr_d2;      // [n] float d2 of the last sweep
   int* corr_pos;       // [n] sorted-array position of the last match (seed of the next search), -1 = none
   float4* c0;          // [n] nearest target point found for cur[i]: xyz + original index (int bits, -1 = none)
   float4* c1;          // [n] runner-up, same layout (nncache.cuh)
   float4* c2;          // [n] third nearest (used when kCacheK == 3)
-  float* lb;           // [n] lower bound on the distance from cur[i] to every target point other than c0, c1
   double* partials;    // [ceil(n / 32)][kNumSums] per-warp sums of one sweep
   IcpState* state;
   int n;

@@ -599,7 +599,6 @@ int run_gicp(b2icp_handle* h, const float* guess16) {
   t.c0 = s.c0.as<float4>();
   t.c1 = s.c1.as<float4>();
   t.c2 = s.c2.as<float4>();
-  t.lb = s.lb.as<float>();
   t.partials = s.partials.as<double>();
   t.state = h->states.as<IcpState>();
   t.n = (int)n;

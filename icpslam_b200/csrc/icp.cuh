@@ -10,8 +10,8 @@
 //   last warp    fixed-order sum over the slabs' partials (deterministic), Umeyama/SVD,
 //                final = T * final, DefaultConvergenceCriteria -> IcpState (solve.cuh)
 // No host round trip: `done` in IcpState turns the remaining launches of the batch into no-ops.
-// HBM bytes per query per iteration: 52 read (running point, two cached neighbours, bound) + 20 written
-// (running point, bound), + 36 written and the target points of the scanned cells when the query is searched;
+// HBM bytes per query per iteration: 48 read (running point with its bound in .w, two cached neighbours) + 16
+// written (running point + bound), + 32 more written and the target points of the scanned cells when the query is searched;
 // the reduction adds 136 B per warp.  Also here: getFitnessScore, the correspondence write-out, transformPointCloud.
 #pragma once
 #include "common.cuh"
@@ -35,7 +35,7 @@ __device__ __forceinline__ void accumulate_pair(double* acc, const float4& q, co
 // One ICP iteration = one launch over all scans of the batch (nncache.cuh explains the certificate).
 //
 // Per-query state carried between iterations (ScanTask): cur (running cloud), c0 / c1 (nearest and
-// runner-up target point: xyz + original index in .w, index -1 = none), lb (distance bound).  All of it
+// runner-up target point: xyz + original index in .w, index -1 = none); the distance bound is cur.w.  All of it
 // is read and written with coalesced, evict-first 16-byte accesses; nothing in the streaming pass depends
 // on a gathered load.  corr_idx / corr_d2 are produced once, after the loop (icp_finalize_corr).
 //
@@ -93,15 +93,14 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) icp_sweep_p2p(co
         p = ld_stream(t.cur + i);
 #pragma unroll
         for (int k = 0; k < kCacheK; ++k) c[k] = ld_stream(cand[k] + i);
-        lb = ld_stream(t.lb + i);
+        lb = p.w;  // the bound travels in the running point's fourth component
       }
-      const float4 q = xform_f(T, p.x, p.y, p.z);
-      st_stream(t.cur + i, q);
+      float4 q = xform_f(T, p.x, p.y, p.z);
+      q.w = 0.0f;
       if (!(isfinite(q.x) && isfinite(q.y) && isfinite(q.z))) {
         atomicOr(&st->pad, 1);  // non-finite source point or transform: reported by the last warp
 #pragma unroll
         for (int k = 0; k < kCacheK; ++k) cand[k][i] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-        t.lb[i] = 0.0f;
       } else if (first) {
         need = true;
       } else {
@@ -130,12 +129,13 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) icp_sweep_p2p(co
         const float d2 = key_d2(k0);
         const float L2 = L > 0.0f ? __fmul_rd(__fmul_rd(L, L), kRelDown) : 0.0f;
         if (fminf(d2, cfg.bound2) < L2) {  // certificate holds: the NN is c0, or nothing is within the bound
-          st_stream(t.lb + i, L);
+          q.w = L;
           if ((d2 < L2) && !((double)d2 > cfg.max2)) accumulate_pair(acc, q, c0, d2);
         } else {
           need = true;
         }
       }
+      st_stream(t.cur + i, q);
     }
     const unsigned bal = __ballot_sync(0xFFFFFFFFu, need);
     if (need) wl_id[warp][wc + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)(qi * 32 + lane);
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) icp_sweep_p2p(co
     st_stream(cand[0] + i, m0);
 #pragma unroll
     for (int k = 1; k < kCacheK; ++k) st_stream(cand[k] + i, top.p[k] >= 0 ? __ldg(t.grid.pts + top.p[k]) : none);
-    st_stream(t.lb + i, top3_bound(top, lrest));
+    st_stream(t.cur + i, make_float4(q.x, q.y, q.z, top3_bound(top, lrest)));
     const float d2 = key_d2(top.k0);
     if ((top.k0 != kInfKey) && !((double)d2 > cfg.max2)) accumulate_pair(acc, q, m0, d2);
   }
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(kSweepThreads) fitness_kernel(const ScanTask* 
     // the last increment and float rounding: the same triangle-inequality test settles most queries here too
     const float4 c = t.cur[i];
     const float step = __fmul_ru(sqrt_fast(sqdist3(q.x, q.y, q.z, c.x, c.y, c.z)), kRelUp);
-    const float L = __fsub_rd(t.lb[i], step);
+    const float L = __fsub_rd(c.w, step);
     const float4* const cand[3] = {t.c0, t.c1, t.c2};
 #pragma unroll
     for (int k = 0; k < kCacheK; ++k) {
