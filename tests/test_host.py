@@ -103,3 +103,21 @@ def test_shims_compile_and_pose_selfcheck(b2lib, tmp_path):
     if not torch.cuda.is_available():             # no CPU fallback behind the shims either
         r = subprocess.run([exe, "odom", "0.2", "/dev/null", "/dev/null"], capture_output=True, text=True)
         assert r.returncode == 3 and "CUDA" in r.stderr
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the oracle timed on the host cores, no GPU, nothing read from /root/reference)
+    prints one JSON line with the keys the driver reads."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, env=dict(os.environ, OMP_NUM_THREADS="1"))
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "icp_scans_per_sec_64k_sweeps_30_iters"
+    assert line["unit"] == "scans/s" and line["higher_is_better"] is True and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert "workload" in line["config"]
