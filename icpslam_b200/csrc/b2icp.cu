@@ -588,6 +588,44 @@ int nn_search_impl(b2icp_handle* h, const float4* d_q, size_t n, int* d_idx, flo
 
 #include "gicp_host.inl"
 
+}  // namespace
+extern "C" {  // defined with the streaming entry points below
+static int submit_impl(b2icp_handle* h, const float* const* src, const size_t* n_src, size_t batch, int with_fitness,
+                       bool from_device);
+static int wait_impl(b2icp_handle* h, b2icp_result* out, size_t capacity, size_t* n_out);
+}
+namespace {
+
+// A synchronous batch against the handle's target is streamed internally: chunks of scans on the slot sets /
+// streams of b2icp_align_batch_submit, up to kStreamSets in flight, so that one call gets the overlap a caller of
+// the streaming pair gets (sparse late iterations of one chunk under the dense first ones of the next, uploads under
+// sweeps).  Results come back in input order.
+int streamed_sync_batch(b2icp_handle* h, const float* const* src, const size_t* n_src, size_t batch, int with_fitness,
+                        b2icp_result* out, bool from_device) {
+  const size_t chunk = (size_t)kSetSlots;
+  size_t submitted = 0, done = 0;
+  h->next_set = 0;  // nothing is in flight: start from the first slot set, so that short batches reuse the same sets
+  int worst = B2ICP_OK;
+  while (done < batch) {
+    while (submitted < batch && h->n_pending < kStreamSets) {
+      const size_t len = std::min(chunk, batch - submitted);
+      int rc = submit_impl(h, src + submitted, n_src + submitted, len, with_fitness, from_device);
+      if (rc) {
+        b2icp_result scratch[kSetSlots];
+        while (h->n_pending) wait_impl(h, scratch, kSetSlots, nullptr);
+        return rc;
+      }
+      submitted += len;
+    }
+    size_t got = 0;
+    int rc = wait_impl(h, out + done, batch - done, &got);
+    if (rc > worst || (rc < 0 && worst == B2ICP_OK)) worst = rc;
+    if (got == 0) return rc ? rc : B2ICP_ERR_CUDA;
+    done += got;
+  }
+  return worst;
+}
+
 // GICP over a batch: the scans run one after the other through slot 0 (the BFGS recursion is driven from the
 // host, gicp_host.inl), with the same target conventions as the point-to-point batch.
 int gicp_batch_impl(b2icp_handle* h, const float* const* src, const size_t* n_src, const float* const* tgt,
@@ -654,6 +692,9 @@ int batch_impl(b2icp_handle* h, const float* const* src, const size_t* n_src, co
   if (h->params.mode == B2ICP_MODE_GICP_BFGS) return gicp_batch_impl(h, src, n_src, tgt, n_tgt, batch, with_fitness, out, from_device);
   if (shared_target && !gslot(h, 0).valid) return fail(h, B2ICP_ERR_NO_TARGET, "no target cloud set");
   if (!shared_target && !tgt[0] && !gslot(h, 0).valid) return fail(h, B2ICP_ERR_NO_TARGET, "pair 0 has no target");
+  // (measured, 128 host sweeps per call: 15.2k scans/s streamed internally against 10.9k as one launch sequence)
+  if (shared_target && batch >= 64 && h->params.profile == 0 && h->n_pending == 0 && getenv("B2ICP_NO_INTERNAL_STREAMING") == nullptr)
+    return streamed_sync_batch(h, src, n_src, batch, with_fitness, out, from_device);
   int worst = B2ICP_OK;
   h->aligned = false;
   // In consecutive-sweep mode pair i (tgt[i] == NULL) registers against src[i-1]; across chunk borders the
@@ -1076,8 +1117,7 @@ int b2icp_align_batch(b2icp_handle* h, const float* const* src, const size_t* n_
 }
 
 // ---- streaming batches: two slot sets, uploads of batch k+1 overlap the sweeps of batch k ----------------
-static int submit_impl(b2icp_handle* h, const float* const* src, const size_t* n_src, size_t batch, int with_fitness,
-                       bool from_device);
+static int wait_impl(b2icp_handle* h, b2icp_result* out, size_t capacity, size_t* n_out);
 int b2icp_align_batch_submit(b2icp_handle* h, const float* const* src, const size_t* n_src, size_t batch, int with_fitness) {
   if (!h || !src || !n_src) return B2ICP_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lk(h->mu);
@@ -1148,6 +1188,9 @@ int b2icp_align_batch_wait(b2icp_handle* h, b2icp_result* out, size_t capacity, 
   if (!h || !out) return B2ICP_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lk(h->mu);
   CK(cudaSetDevice(h->device));
+  return wait_impl(h, out, capacity, n_out);
+}
+static int wait_impl(b2icp_handle* h, b2icp_result* out, size_t capacity, size_t* n_out) {
   if (n_out) *n_out = 0;
   if (h->n_pending == 0) return fail(h, B2ICP_ERR_INVALID_ARG, "no streamed batch in flight");
   const b2icp_handle::Pending pd = h->pending[h->first_pending];

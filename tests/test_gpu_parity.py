@@ -452,6 +452,13 @@ def test_streamed_batches_equal_synchronous_batches(R):
     for a, b in zip(got, ref):
         assert np.array_equal(a.matrix(), b.matrix()) and a.iterations == b.iterations
         assert a.fitness == b.fitness and a.n_corr_last == b.n_corr_last
+    # a synchronous batch of 64 or more scans against the handle's target is streamed internally: same results
+    flat = [s for b in batches for s in b]
+    rc, many = reg.alignBatch([flat[k % len(flat)] for k in range(75)], None, with_fitness=True)
+    assert rc == 0 and len(many) == 75
+    for k, r in enumerate(many):
+        b = ref[k % len(flat)]
+        assert np.array_equal(r.matrix(), b.matrix()) and r.iterations == b.iterations and r.fitness == b.fitness
     for k in range(8):
         assert reg.alignBatchSubmit(batches[k % 4]) == 0                     # eight in flight, each on its own stream
     assert reg.alignBatchSubmit(batches[0]) != 0                             # a ninth is refused
