@@ -83,7 +83,7 @@ struct ScanTask {
   double* partials;    // [ceil(n / 32)][kNumSums] per-warp sums of one sweep
   IcpState* state;
   int n;
-  int pad;             // 1: c0 / c1 / lb hold the certificate of cur (left by the point-to-point loop)
+  int pad;             // 1: c0 / c1 / cur.w hold the certificate of cur (left by the point-to-point loop)
 };
 
 // Per-query state is streamed once per iteration and is larger than what the L2 can keep next to the

@@ -8,7 +8,8 @@
 //
 //   c0, c1   the nearest and second-nearest target point found (coordinates + original index, 16 B each,
 //            stored per query so that the next iteration's test is one coalesced streaming read),
-//   L        a lower bound on the Euclidean distance from the query to EVERY OTHER target point.
+//   L        a lower bound on the Euclidean distance from the query to EVERY OTHER target point (kept in the
+//            fourth component of the running point, so it costs no extra load or store).
 //
 // ICP moves each query a little per iteration.  If the query has moved by `step` since the bound was
 // taken, every other point is still at least L - step away (triangle inequality), so whenever
