@@ -43,6 +43,11 @@ def main():
     _, _, sc = synth.planar_stream(3, 2)
     r = O.align(O.default_params("odometer"), sc[1], sc[0])
     g["c3_planar_p2p"] = {"T": r["T"].tolist(), "iterations": r["iterations"]}
+    v = O.voxel_filter(sw[0], 0.2)
+    g["voxel_0p2"] = {"n": int(len(v)), "sha256": sha(v), "first": v[0].tolist()}
+    m = O.map_insert(None, sw[0], 0.2)
+    a = O.map_insert(m, sw[1], 0.2)
+    g["map_insert_0p2"] = {"n_first": int(len(m)), "n_added": int(len(a)), "sha256": sha(np.concatenate([m, a]))}
     C = O.covariances(sw[0][:512])
     g["cov_512"] = {"trace_sum": float(np.trace(C, axis1=1, axis2=2).sum()), "first": C[0].tolist()}
     with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle_golden.json"), "w") as f:

@@ -221,3 +221,14 @@ def test_map_insert_matches_numpy_restatement(oracle):
     assert len(oracle.map_insert(m, allp, res)) == 0                   # idempotent
     bad = np.array([[np.nan, 0, 0, 1], [1e3, 1e3, 1e3, 1]], np.float32)
     assert np.array_equal(oracle.map_insert(m, bad, res), bad[1:])     # non-finite points are skipped
+
+
+def test_golden_voxel_filter_and_map_insert(oracle):
+    """Regression pins of the two steps either side of the path (made by tests/golden/make_golden.py)."""
+    _, _, sw = synth.sweep_sequence(1, 2, n_beams=64, n_az=64)
+    v = oracle.voxel_filter(sw[0], 0.2)
+    assert len(v) == GOLD["voxel_0p2"]["n"] and sha(v) == GOLD["voxel_0p2"]["sha256"]
+    m = oracle.map_insert(None, sw[0], 0.2)
+    a = oracle.map_insert(m, sw[1], 0.2)
+    assert (len(m), len(a)) == (GOLD["map_insert_0p2"]["n_first"], GOLD["map_insert_0p2"]["n_added"])
+    assert sha(np.concatenate([m, a])) == GOLD["map_insert_0p2"]["sha256"]
