@@ -232,3 +232,56 @@ def test_golden_voxel_filter_and_map_insert(oracle):
     a = oracle.map_insert(m, sw[1], 0.2)
     assert (len(m), len(a)) == (GOLD["map_insert_0p2"]["n_first"], GOLD["map_insert_0p2"]["n_added"])
     assert sha(np.concatenate([m, a])) == GOLD["map_insert_0p2"]["sha256"]
+
+
+def _numpy_icp_witness(src, tgt, max_iter, max_corr=1.0, eps=1e-6):
+    """An independent restatement of pcl::IterativeClosestPoint (SURVEY.md App. A.3) in numpy / scipy: float32
+    in-place transform chain, cKDTree nearest neighbour, gate d2 <= max^2, Umeyama by numpy's SVD in float64,
+    DefaultConvergenceCriteria (iterations, incremental rotation / squared translation, absolute MSE change)."""
+    from scipy.spatial import cKDTree
+    tree = cKDTree(tgt[:, :3].astype(np.float64))
+    cur = src[:, :3].astype(np.float32).copy()
+    final = np.eye(4, dtype=np.float32)
+    prev_mse, it = np.finfo(np.float64).max, 0
+    while True:
+        d, j = tree.query(cur.astype(np.float64), k=1)
+        d2 = ((cur - tgt[j, :3]) ** 2).astype(np.float32)
+        d2 = (d2[:, 0] + d2[:, 1]) + d2[:, 2]
+        keep = d2.astype(np.float64) <= max_corr * max_corr
+        if keep.sum() < 3:
+            return final.astype(np.float64), it, False
+        P, Q = cur[keep].astype(np.float64), tgt[j[keep], :3].astype(np.float64)
+        pc, qc = P.mean(0), Q.mean(0)
+        H = (Q - qc).T @ (P - pc) / len(P)
+        U, _, Vt = np.linalg.svd(H)
+        S = np.diag([1.0, 1.0, -1.0 if np.linalg.det(U) * np.linalg.det(Vt) < 0 else 1.0])
+        Rm = U @ S @ Vt
+        Tinc = np.eye(4)
+        Tinc[:3, :3], Tinc[:3, 3] = Rm, qc - Rm @ pc
+        Tf = Tinc.astype(np.float32)
+        x, y, z = cur[:, 0].copy(), cur[:, 1].copy(), cur[:, 2].copy()
+        for r in range(3):
+            cur[:, r] = ((Tf[r, 0] * x + Tf[r, 1] * y) + Tf[r, 2] * z) + Tf[r, 3]
+        final = (Tf @ final).astype(np.float32)
+        it += 1
+        mse = float(d2[keep].astype(np.float64).mean())
+        if it >= max_iter:
+            return final.astype(np.float64), it, True
+        cos_angle = 0.5 * (float(Tf[0, 0] + Tf[1, 1] + Tf[2, 2]) - 1.0)
+        tr2 = float(Tf[0, 3] ** 2 + Tf[1, 3] ** 2 + Tf[2, 3] ** 2)
+        if (cos_angle >= 1.0 - eps and tr2 <= eps) or abs(mse - prev_mse) < 1e-12:
+            return final.astype(np.float64), it, True
+        prev_mse = mse
+
+
+def test_p2p_loop_matches_an_independent_numpy_restatement(oracle):
+    """The oracle's whole point-to-point loop (not only its parts) against the numpy witness above, on config-1 and
+    config-3 data: same iteration count, same transform to float32 round-off."""
+    _, _, sw = synth.sweep_sequence(1, 3, n_beams=64, n_az=64)
+    _, _, sc = synth.planar_stream(3, 3)
+    for src, tgt, preset, iters in ((sw[1], sw[0], "odometer", 10), (sw[2], sw[1], "mapper", 30), (sc[1], sc[0], "odometer", 10),
+                                    (sc[2], sc[1], "mapper", 30)):
+        o = oracle.align(oracle.default_params(preset), src, tgt)
+        T, it, conv = _numpy_icp_witness(src, tgt, iters)
+        assert o["iterations"] == it and bool(o["converged"]) == conv
+        assert np.abs(o["T"][:3, 3] - T[:3, 3]).max() < 2e-5 and np.abs(o["T"][:3, :3] - T[:3, :3]).max() < 2e-6
