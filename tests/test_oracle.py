@@ -285,3 +285,26 @@ def test_p2p_loop_matches_an_independent_numpy_restatement(oracle):
         T, it, conv = _numpy_icp_witness(src, tgt, iters)
         assert o["iterations"] == it and bool(o["converged"]) == conv
         assert np.abs(o["T"][:3, 3] - T[:3, 3]).max() < 2e-5 and np.abs(o["T"][:3, :3] - T[:3, :3]).max() < 2e-6
+
+
+def test_voxel_filter_matches_a_numpy_restatement(oracle):
+    """pcl::VoxelGrid::applyFilter (SURVEY.md App. A.8) restated with numpy: float32 min corner and inverse leaf,
+    voxel index x-fastest, float32 sums in input order (np.add.at is sequential), one centroid per voxel in ascending
+    index order — bit-identical to the oracle."""
+    _, _, sw = synth.sweep_sequence(3, 1, n_beams=64, n_az=256)
+    cloud = sw[0]
+    for leaf in (0.2, 0.05, 1.0):
+        inv = np.float32(1.0) / np.float32(leaf)
+        xyz = cloud[:, :3].astype(np.float32)
+        min_b = np.floor(xyz.min(axis=0) * inv).astype(np.int64)
+        max_b = np.floor(xyz.max(axis=0) * inv).astype(np.int64)
+        div = max_b - min_b + 1
+        ijk = (np.floor(xyz * inv) - min_b.astype(np.float32)).astype(np.int64)
+        lin = ijk[:, 0] + ijk[:, 1] * div[0] + ijk[:, 2] * div[0] * div[1]
+        uniq, inverse, counts = np.unique(lin, return_inverse=True, return_counts=True)
+        sums = np.zeros((len(uniq), 3), np.float32)
+        np.add.at(sums, inverse, xyz)                       # sequential float32 accumulation, input order
+        ref = np.ones((len(uniq), 4), np.float32)
+        ref[:, :3] = sums / counts[:, None].astype(np.float32)
+        out = oracle.voxel_filter(cloud, leaf)
+        assert out.shape == ref.shape and np.array_equal(out, ref)
