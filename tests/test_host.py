@@ -34,15 +34,63 @@ def test_shard_range_partitions_exactly():
 
 
 def test_compose_odometry_skips_rejected_scans():
+    """A rejected scan keeps the previous pose AND the previous target (reference icp_odometer.cpp:201-209)."""
     T = np.eye(4)
     T[0, 3] = 1.0
     recs = np.zeros((3, replay.RECORD))
     recs[:, :16] = T.reshape(-1)
-    recs[:, 16] = [1, 0, 1]                      # scan 1 did not converge: dropped, pose kept
+    recs[:, 16] = [1, 0, 1]                      # scan 2 did not converge: dropped, pose kept
+    recs[:, 20] = np.nan                         # no fitness asked for
+    recs[:, 21] = [0, 1, 1]                      # pair 2 was (re-)registered against sweep 1, the last accepted one
     poses = replay.compose_odometry(recs)
     assert poses[:, 0].tolist() == [0, 1, 1, 2]
-    poses = replay.compose_odometry(recs, fitness=[0.1, 0.1, 25.0])   # fitness >= 20 rejected
-    assert poses[:, 0].tolist() == [0, 1, 1, 1]
+    recs[:, 16] = 1
+    recs[:, 20] = [0.1, 0.1, 25.0]               # fitness >= 20 rejected
+    recs[:, 21] = [0, 1, 2]
+    poses = replay.compose_odometry(recs)
+    assert poses[:, 0].tolist() == [0, 1, 2, 2]
+    # a table that still registers pair 2 against the REJECTED sweep 2 must not be composed silently
+    recs[:, 20] = [0.1, 25.0, 0.1]
+    with pytest.raises(ValueError):
+        replay.compose_odometry(recs)
+
+
+class _FakeResult:
+    def __init__(self, dx, converged=1, fitness=0.1):
+        T = np.eye(4)
+        T[0, 3] = dx
+        self.T, self.converged, self.iterations, self.n_corr_last, self.mse_last, self.fitness = T.reshape(-1), converged, 3, 100, 0.01, fitness
+
+
+class _FakeRegistration:
+    """Sweeps are 1-point 'clouds' holding their x position: the 'registration' returns the x offset between the
+    two, and rejects (fitness 99) any pair whose source is marked bad."""
+    def __init__(self):
+        self.calls = []
+
+    def alignBatch(self, sources, targets, with_fitness=False):
+        assert with_fitness
+        out, prev = [], None
+        for s, t in zip(sources, targets):
+            t = prev if t is None else t
+            self.calls.append((float(t[0, 0]), float(s[0, 0])))
+            out.append(_FakeResult(s[0, 0] - t[0, 0], fitness=99.0 if s[0, 3] < 0 else 0.1))
+            prev = s
+        return 0, out
+
+
+def test_replay_reregisters_against_the_last_accepted_sweep():
+    """after a rejected scan the reference keeps prev_cloud_, so the NEXT scan is registered against
+    the older cloud.  The batch registers every sweep against its predecessor; fixup_rejected repairs the pairs
+    behind a rejection so that no motion is lost."""
+    xs = [0.0, 1.0, 2.5, 3.0, 4.0]
+    sweeps = [np.array([[x, 0, 0, 1.0]], np.float32) for x in xs]
+    sweeps[2][0, 3] = -1.0                       # sweep 2 is garbage: every registration OF it is rejected
+    reg = _FakeRegistration()
+    records, poses = replay.replay_pairs(sweeps, reg)
+    assert [int(t) for t in records[:, 21]] == [0, 1, 1, 3]       # pair 2 (sweep 3) went back to sweep 1
+    assert reg.calls[-1] == (1.0, 3.0)
+    assert poses[:, 0].tolist() == [0.0, 1.0, 1.0, 3.0, 4.0]      # the motion across the rejected sweep is kept
 
 
 def _gloo_worker(rank, world, port, q):
@@ -57,7 +105,7 @@ def _gloo_worker(rank, world, port, q):
         T = np.eye(4)
         T[0, 3] = i + 1
         local[i - lo, :16] = T.reshape(-1)
-        local[i - lo, 16:] = (1, 5 + i, 100 + i, 0.5)
+        local[i - lo, 16:] = (1, 5 + i, 100 + i, 0.5, 0.25, i)
     table = replay.gather_records(local, n_total)
     poses = replay.compose_odometry(table)
     q.put((rank, table[:, 3].tolist(), table[:, 17].tolist(), poses[-1, 0]))
