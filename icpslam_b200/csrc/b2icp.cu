@@ -121,6 +121,23 @@ struct BatchBuf {
 
 __global__ void zero_counter(unsigned int* c) { *c = 0; }
 
+// IcpState[B] -> b2icp_record[B] (the record sink of streamed batches: b2icp_set_record_sink)
+__global__ void export_records(const IcpState* __restrict__ st, int B, int with_fitness, b2icp_record* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  const IcpState& s = st[i];
+  b2icp_record r;
+  for (int k = 0; k < 16; ++k) r.T[k] = s.final_T[k];
+  r.converged = s.converged;
+  r.iterations = s.iter;
+  r.n_corr_last = s.n_corr;
+  r.status_detail = s.status;
+  r.mse_last = s.mse;
+  r.fitness = (with_fitness && s.status == 0) ? (s.fitness_cnt > 0 ? s.fitness_sum / (double)s.fitness_cnt : 1.7976931348623157e308)
+                                              : __longlong_as_double(0x7FF8000000000000ll);
+  out[i] = r;
+}
+
 }  // namespace
 
 struct b2icp_handle {
@@ -164,8 +181,10 @@ struct b2icp_handle {
   int qpt_override = 0;  // B2ICP_QPT environment variable (tuning only)
   int w_override = 0;    // B2ICP_W: lanes per cooperative search group, 8 or 32 (tuning only)
   int sort_override = -1;  // B2ICP_SORT=0/1 (tuning only)
-  SweepTune tune{0.75f, 2};  // B2ICP_PROBE / B2ICP_JOIN (tuning only)
+  SweepTune tune{0.75f, 4, 1};  // B2ICP_PROBE / B2ICP_JOIN / B2ICP_TILES (tuning only)
   BatchBuf bufs[kStreamSets + 1];  // entry arrays: one per streamed set, the last one for synchronous calls
+  b2icp_record* sink = nullptr;  // b2icp_set_record_sink: device records of streamed batches
+  size_t sink_cap = 0, sink_used = 0;
   double* h_gicp_partials = nullptr;  // pinned read-back of gicp_fdf_kernel's per-CTA sums
   size_t h_gicp_partials_cap = 0;
   long gicp_evals = 0;
@@ -450,7 +469,7 @@ cudaError_t configure_kernels() {
 }
 
 // The entry array of a batch: keys -> stable radix sort by target tile -> fill (sort.cuh).
-int build_entries(b2icp_handle* h, BatchBuf& bb, int B, int slot0, int E, int total_bits, int tile_bits, size_t max_n, bool sorted) {
+int build_entries(b2icp_handle* h, BatchBuf& bb, int B, int slot0, int E, int total_bits, const KeyParams& kp, size_t max_n, bool sorted) {
   CK(bb.ent_src.ensure((size_t)E * sizeof(float4)));
   CK(bb.ent_sid.ensure((size_t)E));
   CK(bb.ent_orig.ensure((size_t)E * sizeof(int)));
@@ -474,7 +493,7 @@ int build_entries(b2icp_handle* h, BatchBuf& bb, int B, int slot0, int E, int to
     unsigned int* k1 = bb.keys1.as<unsigned int>();
     unsigned int* v0 = bb.vals0.as<unsigned int>();
     unsigned int* v1 = bb.vals1.as<unsigned int>();
-    entry_keys<<<dim3((unsigned)((max_n + 255) / 256), (unsigned)B, 1), 256, 0, h->stream>>>(d_tasks, tile_bits, k0, v0);
+    entry_keys<<<dim3((unsigned)((max_n + 255) / 256), (unsigned)B, 1), 256, 0, h->stream>>>(d_tasks, kp, k0, v0);
     h->launches += 1;
     int* hist = bb.hist.as<int>();
     for (int shift = 0; shift < total_bits; shift += kSortBits) {
@@ -506,7 +525,7 @@ int run_batch(b2icp_handle* h, int B, const float* guesses, int slot0 = 0, bool 
   int max_dim = 1;
   // segments of the sort key: scans that share a target grid share a segment
   int seg_grid[kMaxScans], nseg = 0;
-  unsigned long long max_tiles = 1;
+  int dim_x = 1, dim_y = 1, dim_z = 1;
   for (int i = 0; i < B; ++i) {
     ScanSlot& s = slot(h, (size_t)(slot0 + i));
     GridSlot& g = gslot(h, s.grid);
@@ -520,9 +539,9 @@ int run_batch(b2icp_handle* h, int B, const float* guesses, int slot0 = 0, bool 
     if (seg == nseg) {
       seg_grid[nseg++] = s.grid;
       tgt_points += (size_t)g.view.n;
-      const unsigned long long ntx = ((g.view.nx - 1) >> kTileShift) + 1, nty = ((g.view.ny - 1) >> kTileShift) + 1,
-                               ntz = ((g.view.nz - 1) >> kTileShift) + 1;
-      max_tiles = std::max(max_tiles, ntx * nty * ntz);
+      dim_x = std::max(dim_x, g.view.nx);
+      dim_y = std::max(dim_y, g.view.ny);
+      dim_z = std::max(dim_z, g.view.nz);
     }
     ScanTask& t = h->h_tasks[slot0 + i];
     t.grid = g.view;
@@ -550,8 +569,17 @@ int run_batch(b2icp_handle* h, int B, const float* guesses, int slot0 = 0, bool 
   if (total > (size_t)INT32_MAX / 2) return fail(h, B2ICP_ERR_INVALID_ARG, "batch too large");
   const int E = (int)total;
   const bool shared = nseg == 1;
-  const int tile_bits = bits_for(max_tiles), total_bits = tile_bits + bits_for((unsigned long long)nseg);
-  const bool sorted = h->sort_override >= 0 ? h->sort_override != 0 : (E >= kSortMinEntries && total_bits <= 32);
+  KeyParams kp{};
+  const int seg_bits = bits_for((unsigned long long)nseg);
+  for (kp.drop = 0;; ++kp.drop) {  // the full Morton code fits 32 bits for every grid the dense cell table allows
+    kp.bx = bits_for((unsigned long long)((dim_x - 1) >> kp.drop) + 1);
+    kp.by = bits_for((unsigned long long)((dim_y - 1) >> kp.drop) + 1);
+    kp.bz = bits_for((unsigned long long)((dim_z - 1) >> kp.drop) + 1);
+    kp.cell_bits = kp.bx + kp.by + kp.bz;
+    if (kp.cell_bits + seg_bits <= 32) break;
+  }
+  const int total_bits = kp.cell_bits + seg_bits;
+  const bool sorted = h->sort_override >= 0 ? h->sort_override != 0 : E >= kSortMinEntries;
   // the entry arrays exist before the tasks are uploaded: the tasks point into them
   CK(bb.cur.ensure((size_t)E * sizeof(float4)));
   CK(bb.c0.ensure((size_t)E * sizeof(float4)));
@@ -579,7 +607,7 @@ int run_batch(b2icp_handle* h, int B, const float* guesses, int slot0 = 0, bool 
     CK(cudaEventRecord(h->events[0], h->stream));
   }
   {
-    int rc = build_entries(h, bb, B, slot0, E, total_bits, tile_bits, max_n, sorted);
+    int rc = build_entries(h, bb, B, slot0, E, total_bits, kp, max_n, sorted);
     if (rc) return rc;
   }
   BatchView& bv = bb.view;
@@ -961,6 +989,7 @@ int b2icp_create(const b2icp_params* p, b2icp_handle** out) {
   if (const char* e = getenv("B2ICP_SORT")) h->sort_override = atoi(e);
   if (const char* e = getenv("B2ICP_PROBE")) h->tune.probe_frac = (float)atof(e);
   if (const char* e = getenv("B2ICP_JOIN")) h->tune.join_d = atoi(e);
+  if (const char* e = getenv("B2ICP_TILES")) h->tune.use_tiles = atoi(e);
   slot(h, 0);
   gslot(h, 0);
   bool ok = cudaSetDevice(h->device) == cudaSuccess && configure_kernels() == cudaSuccess &&
@@ -1304,6 +1333,11 @@ static int submit_impl(b2icp_handle* h, const float* const* src, const size_t* n
     for (int i = 0; i < B && !rc; ++i) rc = enqueue_fitness(h, slot0 + i, DBL_MAX);
   h->stream = saved;
   if (rc) return rc;
+  if (h->sink && h->sink_used + (size_t)B <= h->sink_cap) {
+    export_records<<<1, 64, 0, cs>>>(h->states.as<IcpState>() + slot0, B, with_fitness, h->sink + h->sink_used);
+    h->sink_used += (size_t)B;
+    h->launches += 1;
+  }
   CK(cudaMemcpyAsync(h->h_states + slot0, h->states.as<IcpState>() + slot0, sizeof(IcpState) * B, cudaMemcpyDeviceToHost, cs));
   CK(cudaEventRecord(h->set_done[set], cs));
   h->pending[(h->first_pending + h->n_pending) % kStreamSets] = {set, B, with_fitness};
@@ -1341,6 +1375,22 @@ static int wait_impl(b2icp_handle* h, b2icp_result* out, size_t capacity, size_t
   h->timing.kernel_launches = h->launches;
   if (n_out) *n_out = (size_t)pd.B;
   return worst;
+}
+
+int b2icp_set_record_sink(b2icp_handle* h, b2icp_record* d_records, size_t capacity) {
+  if (!h) return B2ICP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (h->n_pending) return fail(h, B2ICP_ERR_INVALID_ARG, "record sink changed while batches are in flight");
+  h->sink = d_records;
+  h->sink_cap = d_records ? capacity : 0;
+  h->sink_used = 0;
+  return B2ICP_OK;
+}
+int b2icp_record_sink_count(b2icp_handle* h, size_t* n) {
+  if (!h || !n) return B2ICP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  *n = h->sink_used;
+  return B2ICP_OK;
 }
 
 int b2icp_align_batch_device(b2icp_handle* h, const float* const* d_src, const size_t* n_src,

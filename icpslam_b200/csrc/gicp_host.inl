@@ -467,6 +467,7 @@ int run_gicp(b2icp_handle* h, const float* guess16) {
   const size_t n = s.src.n;
   int rc = ensure_slot_work(h, s);
   if (rc) return rc;
+  CK(s.corr_pos.ensure(n * sizeof(int)));  // sorted position of the last match: the seed of the next search
   // covariances: target (cached with its grid) and source (own temporary grid)
   if (!g.cov_valid) {
     rc = compute_covariances(h, g, (size_t)g.view.n, g.cov);

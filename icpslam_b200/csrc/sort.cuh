@@ -1,12 +1,12 @@
-// sort.cuh — the ENTRY ARRAY of a batch: every query of every scan of the batch, ordered by the tile of the
-// target grid it falls in (tile = 2x2x2 cells, x-fastest tile order, scans interleaved).
+// sort.cuh — the ENTRY ARRAY of a batch: every query of every scan of the batch, ordered by the Z-order (Morton)
+// code of the target-grid cell it falls in (scans interleaved).
 //
 // Why: the neighbour search of icp_sweep_coop (sweep.cuh) is warp-cooperative — the 32 (or 8) queries of a group
 // share ONE staged set of candidate target points.  That only pays when the queries of a group are close
 // together, and how close they are is set by the QUERY density.  One HDL-64 sweep has ~8 returns per m^2 of
 // surface against ~25 map points per m^2; the 32 sweeps of a batch together have ~250 per m^2.  Sorting the
-// batch's queries by tile ACROSS scans turns a group of 32 consecutive entries into "the queries of ~one tile",
-// whose candidate set is the ~25 map points around that tile (reference: the per-scan loop around
+// batch's queries by cell ACROSS scans turns a group of 32 consecutive entries into "the queries of ~one cell",
+// whose candidate set is the ~25 map points around that cell (reference: the per-scan loop around
 // icp.align(), src/icpslam/icp_odometer.cpp:198 — the scans are independent, so any order is legal).
 //
 // The sort is a stable LSD radix sort (11-bit digits) written for determinism: equal keys keep their input
@@ -25,10 +25,31 @@ constexpr int kSortThreads = 256;
 constexpr int kSortWarps = kSortThreads / 32;
 constexpr int kSortPerWarp = 512;                        // consecutive elements owned by one warp
 constexpr int kSortChunk = kSortWarps * kSortPerWarp;    // 4096 elements per CTA
-constexpr int kTileShift = 1;                            // tile = 2 cells per axis
 
-// key of every query: (segment << tile_bits) | tile of guess * p in the scan's target grid; value = global id
-__global__ void __launch_bounds__(256) entry_keys(const ScanTask* __restrict__ tasks, int tile_bits,
+// Z-order (Morton) code of a cell: bit l of x, y, z interleaved from the low bits up; axes that have run out of bits
+// are skipped, so the code has bits.x + bits.y + bits.z bits.  Consecutive codes are close in space at every scale,
+// which is what keeps the union box of a warp's compacted work list small.
+__device__ __forceinline__ unsigned int morton_key(int cx, int cy, int cz, int bx, int by, int bz) {
+  unsigned int key = 0;
+  int pos = 0;
+  const int top = max(bx, max(by, bz));
+  for (int l = 0; l < top; ++l) {
+    if (l < bx) key |= (unsigned int)((cx >> l) & 1) << pos++;
+    if (l < by) key |= (unsigned int)((cy >> l) & 1) << pos++;
+    if (l < bz) key |= (unsigned int)((cz >> l) & 1) << pos++;
+  }
+  return key;
+}
+
+struct KeyParams {
+  int bx, by, bz;  // bits per axis after `drop`
+  int drop;        // low cell-coordinate bits left out of the key (only when the full code would not fit 32 bits)
+  int cell_bits;   // bx + by + bz: the segment sits above them
+};
+
+// key of every query: (segment << cell_bits) | Morton code of the cell of guess * p in the scan's target grid;
+// value = global id (ent_off + index)
+__global__ void __launch_bounds__(256) entry_keys(const ScanTask* __restrict__ tasks, KeyParams kp,
                                                   unsigned int* __restrict__ keys, unsigned int* __restrict__ vals) {
   const ScanTask& t = tasks[blockIdx.y];
   const int i = blockIdx.x * 256 + threadIdx.x;
@@ -36,12 +57,10 @@ __global__ void __launch_bounds__(256) entry_keys(const ScanTask* __restrict__ t
   const float4 p = __ldg(t.src + i);
   const float4 q = xform_f(t.state->Tinc, p.x, p.y, p.z);  // Tinc holds the initial guess before the first sweep
   const GridView& g = t.grid;
-  const int tx = cell_coord(q.x, g.ox, g.inv_cell, g.nx) >> kTileShift;
-  const int ty = cell_coord(q.y, g.oy, g.inv_cell, g.ny) >> kTileShift;
-  const int tz = cell_coord(q.z, g.oz, g.inv_cell, g.nz) >> kTileShift;
-  const int ntx = ((g.nx - 1) >> kTileShift) + 1, nty = ((g.ny - 1) >> kTileShift) + 1;
-  const unsigned int tile = (unsigned int)((tz * nty + ty) * ntx + tx);
-  keys[t.ent_off + i] = ((unsigned int)t.seg << tile_bits) | tile;
+  const int cx = cell_coord(q.x, g.ox, g.inv_cell, g.nx) >> kp.drop;
+  const int cy = cell_coord(q.y, g.oy, g.inv_cell, g.ny) >> kp.drop;
+  const int cz = cell_coord(q.z, g.oz, g.inv_cell, g.nz) >> kp.drop;
+  keys[t.ent_off + i] = ((unsigned int)t.seg << kp.cell_bits) | morton_key(cx, cy, cz, kp.bx, kp.by, kp.bz);
   vals[t.ent_off + i] = (unsigned int)(t.ent_off + i);
 }
 

@@ -45,12 +45,15 @@ struct SweepSmem {  // carved out of dynamic shared memory by sweep_smem_bytes()
   float* T;                   // [kMaxScans][kTStride]
   GridView* grid;             // [kMaxScans] (per-scan grids; unused by SHARED kernels)
   unsigned short* wl;         // [warps][32 * QPT]
+  int* tcs;                   // [warps][kTileRows * kTileW] cell-table slices of the warp's tile
+  unsigned short* toff;       // [warps][kTileRows] first slot of every tile row
   unsigned char* flag;        // [kMaxScans]: bit 0 = done, bit 1 = first sweep
 };
 
 __host__ __device__ constexpr size_t sweep_smem_bytes(int qpt, bool shared_grid) {
   return (size_t)(kSweepThreads / 32) * kCoopCap * 16 + (size_t)(kSweepThreads / 32) * 8 + (size_t)kMaxScans * kTStride * 4 +
-         (shared_grid ? 0 : (size_t)kMaxScans * sizeof(GridView)) + (size_t)(kSweepThreads / 32) * 32 * qpt * 2 + kMaxScans + 64;
+         (shared_grid ? 0 : (size_t)kMaxScans * sizeof(GridView)) + (size_t)(kSweepThreads / 32) * 32 * qpt * 2 +
+         (size_t)(kSweepThreads / 32) * kTileRows * (kTileW * 4 + 2) + kMaxScans + 64;
 }
 
 __device__ __forceinline__ SweepSmem sweep_carve(unsigned char* base, int qpt, bool shared_grid) {
@@ -66,6 +69,10 @@ __device__ __forceinline__ SweepSmem sweep_carve(unsigned char* base, int qpt, b
   base += shared_grid ? 0 : kMaxScans * sizeof(GridView);
   s.wl = reinterpret_cast<unsigned short*>(base);
   base += (size_t)kWarps * 32 * qpt * 2;
+  s.tcs = reinterpret_cast<int*>(base);
+  base += (size_t)kWarps * kTileRows * kTileW * 4;
+  s.toff = reinterpret_cast<unsigned short*>(base);
+  base += (size_t)kWarps * kTileRows * 2;
   s.flag = base;
   return s;
 }
@@ -73,6 +80,7 @@ __device__ __forceinline__ SweepSmem sweep_carve(unsigned char* base, int qpt, b
 struct SweepTune {
   float probe_frac;  // radius of the first, unseeded pass as a fraction of the cell edge
   int join_d;        // cells of slack inside which a lane joins its group's pass
+  int use_tiles;     // stage 1 of phase B (slab tiles) on / off
 };
 
 // QPT: queries per lane (a warp owns a slab of 32 * QPT consecutive entries).  W: lanes per cooperative group.
@@ -103,14 +111,20 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) icp_sweep_coop(B
   unsigned long long* const bar = sm.bar + warp;
   unsigned int phase = 0;
 
-  // ---- phase A: transform + certificate, failures -> the warp's work list
+  // ---- phase A: transform + certificate, failures -> the warp's work list; the union of the failures' cell boxes
   int wc = 0;
+  int uxa = 0x7FFFFFFF, uxb = -1, uya = 0x7FFFFFFF, uyb = -1, uza = 0x7FFFFFFF, uzb = -1;  // warp-uniform
+  int slab_sid = -1;   // scan of the first failure (per-scan grids: a tile serves one grid)
+  bool mixed = false;  // failures of more than one scan
 #pragma unroll 1
   for (int qi = 0; qi < QPT; ++qi) {
     const int e = base + qi * 32 + lane;
     bool need = false;
+    int sid = 0;
+    float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+    float seed = INFINITY;
     if (e < bv.E) {
-      const int sid = __ldg(bv.ent_sid + e);
+      sid = __ldg(bv.ent_sid + e);
       const unsigned int fl = sm.flag[sid];
       if (!(fl & 1u)) {
         const bool first = (fl & 2u) != 0;
@@ -125,7 +139,7 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) icp_sweep_coop(B
           c0 = ld_stream(bv.c0 + e);
           c1 = ld_stream(bv.c1 + e);
         }
-        float4 q = xform_f(T, p.x, p.y, p.z);
+        q = xform_f(T, p.x, p.y, p.z);
         q.w = 0.0f;
         if (!(isfinite(q.x) && isfinite(q.y) && isfinite(q.z))) {
           atomicOr(&tasks[sid].state->pad, 1);  // non-finite source point or transform: reported by the reduce
@@ -148,31 +162,110 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) icp_sweep_coop(B
           }
           const float d2 = key_d2(k1 < k0 ? k1 : k0);
           const float L2 = L > 0.0f ? __fmul_rd(__fmul_rd(L, L), kRelDown) : 0.0f;
-          if (fminf(d2, cfg.bound2) < L2) q.w = L;  // certificate holds: the NN is c0, or nothing lies within the gate
-          else need = true;
+          if (fminf(d2, cfg.bound2) < L2) {
+            q.w = L;  // certificate holds: the NN is c0, or nothing lies within the gate
+          } else {
+            need = true;
+            seed = d2;  // distance to the nearer cached point: a certain search radius (+inf: none cached)
+          }
         }
         st_stream(bv.cur + e, q);
       }
     }
     const unsigned int bal = __ballot_sync(0xFFFFFFFFu, need);
-    if (need) wl[wc + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)(qi * 32 + lane);
-    wc += __popc(bal);
+    if (bal) {
+      if (need) wl[wc + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)(qi * 32 + lane);
+      wc += __popc(bal);
+      // the box this failure will search (the same expression phase B evaluates), into the slab's union
+      if (slab_sid < 0) slab_sid = __shfl_sync(0xFFFFFFFFu, sid, __ffs(bal) - 1);
+      mixed = mixed || __any_sync(0xFFFFFFFFu, need && sid != slab_sid);
+      const GridView& g = SHARED ? bv.grid : sm.grid[slab_sid];
+      const float pr = tune.probe_frac * g.cell;
+      const CellBox bx = cell_box(g, q.x, q.y, q.z, seed < INFINITY ? seed : fmul(pr, pr), cfg.bound2, cfg.margin_frac * g.cell,
+                                  cfg.max_rings);
+      uxa = min(uxa, __reduce_min_sync(0xFFFFFFFFu, need ? bx.xa : 0x7FFFFFFF));
+      uxb = max(uxb, __reduce_max_sync(0xFFFFFFFFu, need ? bx.xb : -1));
+      uya = min(uya, __reduce_min_sync(0xFFFFFFFFu, need ? bx.ya : 0x7FFFFFFF));
+      uyb = max(uyb, __reduce_max_sync(0xFFFFFFFFu, need ? bx.yb : -1));
+      uza = min(uza, __reduce_min_sync(0xFFFFFFFFu, need ? bx.za : 0x7FFFFFFF));
+      uzb = max(uzb, __reduce_max_sync(0xFFFFFFFFu, need ? bx.zb : -1));
+    }
   }
   __syncwarp();
   if (wc == 0) return;
   if (lane == 0) atomicAdd(&tasks[__ldg(bv.ent_sid + base)].state->unresolved, (unsigned int)wc);  // statistics (per batch)
 
-  // ---- phase B: the work list, 32 entries at a time, searched cooperatively
-  const float4 none = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-  for (int e0 = 0; e0 < wc; e0 += 32) {
-    const bool have = e0 + lane < wc;
+  // ---- phase B, stage 1: the union box of the work list staged once (bulk-async copies of its rows), every lane
+  // scanning its own box out of shared memory.  Queries whose probe radius proved too small, and slabs whose
+  // union does not fit a tile, go to stage 2.
+  int wc2 = wc;
+  bool use_cache_always = false;
+  if (tune.use_tiles && (SHARED || !mixed)) {
+    const GridView& g = SHARED ? bv.grid : sm.grid[slab_sid];
+    int* const tcs = sm.tcs + warp * (kTileRows * kTileW);
+    unsigned short* const toff = sm.toff + warp * kTileRows;
+    if (tile_stage(g, uxa, uxb, uya, uyb, uza, uzb, wbuf, tcs, toff, bar, phase)) {
+      Tile tile;
+      tile.buf = wbuf;
+      tile.cs = tcs;
+      tile.off = toff;
+      tile.xa = uxa;
+      tile.ya = uya;
+      tile.za = uza;
+      tile.ny = uyb - uya + 1;
+      wc2 = 0;
+      for (int e0 = 0; e0 < wc; e0 += 32) {
+        const bool have = e0 + lane < wc;
+        const unsigned short id = have ? wl[e0 + lane] : (unsigned short)0;
+        const int e = base + (int)id;
+        bool again = false;
+        if (have) {
+          const int sid = (int)__ldg(bv.ent_sid + e);
+          const float4 q = bv.cur[e];
+          float seed = INFINITY;
+          if (!(sm.flag[sid] & 2u)) {  // radius from the cached pair (the list keeps ids only; both points are L2-hot)
+            const float4 a = bv.c0[e], b = bv.c1[e];
+            if (__float_as_int(a.w) >= 0) seed = sqdist3(q.x, q.y, q.z, a.x, a.y, a.z);
+            if (__float_as_int(b.w) >= 0) seed = fminf(seed, sqdist3(q.x, q.y, q.z, b.x, b.y, b.z));
+          }
+          const float pr = tune.probe_frac * g.cell;
+          const CellBox bx = cell_box(g, q.x, q.y, q.z, seed < INFINITY ? seed : fmul(pr, pr), cfg.bound2,
+                                      cfg.margin_frac * g.cell, cfg.max_rings);
+          CoopTop top;
+          tile_search(g, tile, q.x, q.y, q.z, bx, top);
+          float bound = coop_bound(top);
+          if (!(seed < INFINITY)) {  // probe radius: exact only if the best candidate beats everything outside the box
+            const float best = key_d2(top.k0);
+            const bool exact = !(top.lrest < INFINITY) ||
+                               (top.k0 != kInfKey && best < __fmul_rd(__fmul_rd(top.lrest, top.lrest), kRelDown));
+            if (!exact) {  // what was found becomes the cached pair: stage 2 takes its radius from it
+              again = true;
+              bound = 0.0f;
+            }
+          }
+          st_stream(bv.c0 + e, coop_c0(top));
+          st_stream(bv.c1 + e, coop_c1(top));
+          st_stream(bv.cur + e, make_float4(q.x, q.y, q.z, bound));
+        }
+        const unsigned int bal = __ballot_sync(0xFFFFFFFFu, again);  // (also orders this round's reads of wl before the writes)
+        if (again) wl[wc2 + __popc(bal & ((1u << lane) - 1u))] = id;
+        wc2 += __popc(bal);
+      }
+      use_cache_always = true;
+      __syncwarp();
+    }
+  }
+
+  // ---- phase B, stage 2: what is left, 32 entries at a time, searched cooperatively (coop.cuh)
+  for (int e0 = 0; e0 < wc2; e0 += 32) {
+    const bool have = e0 + lane < wc2;
     const int e = have ? base + (int)wl[e0 + lane] : base;
     const int sid = have ? (int)__ldg(bv.ent_sid + e) : -1;
     float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
     float seed = INFINITY;
     if (have) {
       q = bv.cur[e];
-      if (!(sm.flag[sid] & 2u)) {  // radius from the cached pair (the list keeps ids only; both points are L2-hot)
+      if (use_cache_always || !(sm.flag[sid] & 2u)) {
         const float4 a = bv.c0[e], b = bv.c1[e];
         if (__float_as_int(a.w) >= 0) seed = sqdist3(q.x, q.y, q.z, a.x, a.y, a.z);
         if (__float_as_int(b.w) >= 0) seed = fminf(seed, sqdist3(q.x, q.y, q.z, b.x, b.y, b.z));
@@ -223,7 +316,6 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) icp_sweep_coop(B
       st_stream(bv.cur + e, make_float4(q.x, q.y, q.z, coop_bound(top)));
     }
   }
-  (void)none;
 }
 
 // K3 + K4: sums of one iteration of one scan over a fixed tree, then the solve (last CTA of the scan).
@@ -239,16 +331,29 @@ __global__ void __launch_bounds__(256) icp_reduce(const ScanTask* __restrict__ t
   double acc[kNumSums];
 #pragma unroll
   for (int c = 0; c < kNumSums; ++c) acc[c] = 0.0;
-#pragma unroll 2
-  for (int k = 0; k < kReduceUnit / 32; ++k) {
-    const int i = unit * kReduceUnit + k * 32 + lane;
-    if (i < t.n) {
-      const int e = __ldg(t.pos + i);
-      const float4 q = __ldcg(t.cur + e);
-      const float4 m = __ldcg(t.c0 + e);
-      if (__float_as_int(m.w) >= 0) {
-        const float d2 = sqdist3(q.x, q.y, q.z, m.x, m.y, m.z);
-        if (!((double)d2 > cfg.max2)) accumulate_pair(acc, q, m, d2);
+  // four queries at a time: their entry positions first, then the eight gathers, so that a lane has all of its
+  // loads of a round in flight before the first sum (the gathers are L2 hits: the sweep has just written them)
+#pragma unroll 1
+  for (int k0 = 0; k0 < kReduceUnit / 32; k0 += 4) {
+    int e[4];
+    float4 q[4], m[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = unit * kReduceUnit + (k0 + k) * 32 + lane;
+      e[k] = i < t.n ? __ldg(t.pos + i) : -1;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (e[k] >= 0) {
+        q[k] = __ldcg(t.cur + e[k]);
+        m[k] = __ldcg(t.c0 + e[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (e[k] >= 0 && __float_as_int(m[k].w) >= 0) {
+        const float d2 = sqdist3(q[k].x, q[k].y, q[k].z, m[k].x, m[k].y, m[k].z);
+        if (!((double)d2 > cfg.max2)) accumulate_pair(acc, q[k], m[k], d2);
       }
     }
   }

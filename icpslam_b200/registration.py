@@ -86,6 +86,12 @@ class Timing(C.Structure):
     ]
 
 
+# b2icp_record (include/b2icp.h): the 96-byte per-scan record of the device record sink
+RECORD_DTYPE = np.dtype([("T", np.float32, (16,)), ("converged", np.int32), ("iterations", np.int32),
+                         ("n_corr_last", np.int32), ("status_detail", np.int32), ("mse_last", np.float64),
+                         ("fitness", np.float64)])
+assert RECORD_DTYPE.itemsize == 96
+
 EXPORTS = [
     "b2icp_default_params", "b2icp_create", "b2icp_destroy", "b2icp_set_params", "b2icp_set_target",
     "b2icp_set_source", "b2icp_set_target_device", "b2icp_set_source_device", "b2icp_promote_source_to_target",
@@ -93,6 +99,7 @@ EXPORTS = [
     "b2icp_transform_cloud", "b2icp_transform_cloud_f", "b2icp_align_batch", "b2icp_align_batch_device",
     "b2icp_set_stream", "b2icp_compute_covariances", "b2icp_voxel_filter", "b2icp_get_timing",
     "b2icp_align_batch_submit", "b2icp_align_batch_submit_device", "b2icp_align_batch_wait",
+    "b2icp_set_record_sink", "b2icp_record_sink_count",
     "b2icp_map_reset", "b2icp_map_insert", "b2icp_map_insert_device", "b2icp_map_size", "b2icp_map_download",
     "b2icp_map_nearest", "b2icp_set_target_map", "b2icp_mapper_register", "b2icp_mapper_grow",
     "b2icp_get_grid_info", "b2icp_host_alloc", "b2icp_host_free", "b2icp_last_error", "b2icp_status_string",
@@ -140,6 +147,8 @@ def load_library() -> C.CDLL:
     L.b2icp_align_batch_submit.argtypes = [vp, vp, vp, C.c_size_t, C.c_int]
     L.b2icp_align_batch_submit_device.argtypes = [vp, vp, vp, C.c_size_t, C.c_int]
     L.b2icp_align_batch_wait.argtypes = [vp, vp, C.c_size_t, szp]
+    L.b2icp_set_record_sink.argtypes = [vp, vp, C.c_size_t]
+    L.b2icp_record_sink_count.argtypes = [vp, szp]
     L.b2icp_map_reset.argtypes = [vp, C.c_double]
     L.b2icp_map_insert.argtypes = [vp, vp, C.c_size_t, szp]
     L.b2icp_map_insert_device.argtypes = [vp, vp, C.c_size_t, szp]
@@ -394,6 +403,16 @@ class Registration:
         rc = self._L.b2icp_align_batch_wait(self._h, res, n, C.byref(got))
         self._inflight = pend[1:]
         return rc, list(res)[: got.value]
+
+    def setRecordSink(self, device_ptr, capacity: int) -> None:
+        """b2icp_set_record_sink: streamed batches append one 96-byte b2icp_record per scan at `device_ptr`
+        (device memory, `capacity` records); None switches the sink off."""
+        self._check(self._L.b2icp_set_record_sink(self._h, device_ptr, capacity if device_ptr else 0), "set_record_sink")
+
+    def recordSinkCount(self) -> int:
+        n = C.c_size_t()
+        self._check(self._L.b2icp_record_sink_count(self._h, C.byref(n)), "record_sink_count")
+        return int(n.value)
 
     def alignBatchDevice(self, src_ptrs, n_src, with_fitness: bool = False):
         """b2icp_align_batch_device against the current target; src_ptrs are device addresses."""

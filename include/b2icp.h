@@ -208,6 +208,26 @@ int b2icp_align_batch_submit_device(b2icp_handle* h, const float* const* d_src, 
                                     int with_fitness);
 int b2icp_align_batch_wait(b2icp_handle* h, b2icp_result* out, size_t capacity, size_t* n_out);
 
+/* The fixed-size per-scan record that travels between ranks in offline replay (the ONLY
+ * exchange of the path is the gather of the per-scan rigid transforms back to rank 0, which then composes
+ * pose_i = pose_{i-1} o T_i as icp_odometer.cpp:111-113 does). */
+typedef struct b2icp_record {
+  float T[16];           /* getFinalTransformation(): Matrix4f, row-major, source -> target */
+  int32_t converged;     /* hasConverged() */
+  int32_t iterations;
+  int32_t n_corr_last;
+  int32_t status_detail;
+  double mse_last;
+  double fitness;        /* getFitnessScore(); NaN when the batch did not ask for it */
+} b2icp_record;
+/* Record sink in DEVICE memory: every streamed batch submitted after this call appends one b2icp_record per scan
+ * at d_records (submission order, stream-ordered before the batch signals completion), so that a replay can hand
+ * the records of many batches to ONE collective (ncclAllGather) without a host round trip or a per-batch barrier.
+ * d_records == NULL switches the sink off.  b2icp_record_sink_count: records written by the batches waited for
+ * so far plus those still in flight. */
+int b2icp_set_record_sink(b2icp_handle* h, b2icp_record* d_records, size_t capacity);
+int b2icp_record_sink_count(b2icp_handle* h, size_t* n);
+
 /* ---- the mapper's point map (OctreeMapper::map_octree_ / map_cloud_, octree_mapper.h:82-83) --------------
  * b2icp_map_reset          OctreeMapper::resetMap (octree_mapper.cpp:56-60): empty map at `resolution`.
  * b2icp_map_insert         OctreeMapper::addPointsToMap (octree_mapper.cpp:63-71): a point enters the map iff
@@ -259,5 +279,6 @@ int b2icp_version(void);
 static_assert(sizeof(b2icp_params) == 88, "b2icp_params layout is part of the ABI");
 static_assert(sizeof(b2icp_result) == 160, "b2icp_result layout is part of the ABI");
 static_assert(sizeof(b2icp_timing) == 48, "b2icp_timing layout is part of the ABI");
+static_assert(sizeof(b2icp_record) == 96, "b2icp_record layout is part of the ABI");
 #endif
 #endif /* B2ICP_H_ */
