@@ -5,17 +5,22 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
 
-A "step" is one pass of the hot path over one batch of B sweeps: b2icp_align_batch (one fused sweep
-launch per ICP iteration for the whole batch) against the resident map, then — when N > 1 — the NCCL
-gather of the per-scan rigid transforms (the only exchange the path has).  Weak
-scaling: every rank owns B sweeps; the map is replicated.
+A "step" is one pass of the hot path over one batch of B sweeps (b2icp_align_batch_submit / _wait against the
+resident map; one fused sweep launch per ICP iteration for the whole batch).  Steps rotate through --sets (4)
+DISTINCT sets of B sweeps.  Weak scaling: every rank owns its own sets; the map is replicated.  The only exchange
+of the path is the gather of the per-scan rigid transforms: the library appends every
+scan's 96-byte record to a device buffer (b2icp_set_record_sink) and ONE ncclAllGather on a side stream, after the
+last step and inside the timed region, hands all K*B records of every rank to every rank — no per-step barrier.
 
-  value   scans/s with the sweeps already resident in HBM (device pointers through the C ABI)
-  e2e     scans/s through the same C ABI with pinned HOST buffers: H2D of every sweep and D2H of the
-          results inside the timed region
-  roofline  fused sweep kernel: algorithmic bytes / CUDA-event launch time, vs the measured HBM peak
+  value     scans/s with the sweeps already resident in HBM (device pointers through the C ABI)
+  e2e       scans/s through the same C ABI with pinned HOST buffers: H2D of every sweep and D2H of the
+            results inside the timed region
+  roofline  fused sweep kernel: algorithmic bytes / CUDA-event launch time, vs the measured HBM peak; nested in it:
+            nn_search (the stand-alone search kernel), pairs (BASELINE configs[3]: consecutive 64k-pt sweeps, each
+            registered against its predecessor, 64 pairs per rank + the gather of the records), details
+  parity    the GPU transforms / iteration counts of the --cpu-sample sweeps against the CPU oracle's (same run)
   cpu_baseline  the CPU oracle (kind "port": the reference's PCL path cannot be built here) timed on
-          this box's host cores on a bounded sample of the same workload
+            this box's host cores on a bounded sample of the same workload
 
 `--impl reference` times the oracle alone (all host threads) on the same workload and prints the
 same line with "impl": "reference".  Nothing here reads /root/reference.
@@ -44,6 +49,8 @@ MAX_ITERS = 30
 METRIC = "icp_scans_per_sec_64k_sweeps_30_iters"
 UNIT = "scans/s"
 STATE_BYTES = 192      # sizeof(IcpState): what comes back per scan
+N_SETS = 4             # distinct sets of sweeps the steps rotate through
+PAIRS_PER_RANK = 64    # configs[3] leg: consecutive pairs per rank (8 ranks = the 512 sweeps of BASELINE configs[3])
 
 
 def log(*a):
@@ -55,35 +62,36 @@ def log(*a):
 # ------------------------------------------------------------------------------------------------
 def load_workload(first: int, count: int, cache_dir: str = "/tmp/b2icp_bench_cache"):
     """(map[500000,4], [count sweeps already in the map frame up to a small odometry error])."""
-    return prepare_workloads([first], count, cache_dir)[first]
+    return prepare_workloads([(first, 0)], count, cache_dir)[(first, 0)]
 
 
-def prepare_workloads(firsts, count: int, cache_dir: str = "/tmp/b2icp_bench_cache") -> dict:
-    """{first: (map, sweeps)} for every start index in `firsts`; the map is generated once and all of
-    it is cached under /tmp as .npy so that back-to-back runs on one box skip the ray casting."""
+def prepare_workloads(keys, count: int, cache_dir: str = "/tmp/b2icp_bench_cache") -> dict:
+    """{(first, variant): (map, sweeps)}: `count` sweeps from pose index `first` on; variant v > 0 re-draws the range
+    noise and the odometry error of the same poses.  The map is generated once and all of it is cached under /tmp
+    as .npy so that back-to-back runs on one box skip the ray casting."""
     os.makedirs(cache_dir, exist_ok=True)
     mpath = os.path.join(cache_dir, f"map_c{CONFIG_ID}_{N_MAP}.npy")
-    qpaths = {f: os.path.join(cache_dir, f"q_c{CONFIG_ID}_{f}_{count}.npy") for f in firsts}
+    qpaths = {k: os.path.join(cache_dir, f"q_c{CONFIG_ID}_{k[0]}_{count}" + (f"_v{k[1]}" if k[1] else "") + ".npy") for k in keys}
     out, m = {}, None
-    for f in firsts:
-        if os.path.exists(mpath) and os.path.exists(qpaths[f]):
-            out[f] = (np.load(mpath), list(np.load(qpaths[f])))
+    for k in keys:
+        if os.path.exists(mpath) and os.path.exists(qpaths[k]):
+            out[k] = (np.load(mpath), list(np.load(qpaths[k])))
             continue
         t0 = time.time()
         if m is None:
             m = synth.build_local_map(CONFIG_ID, n_points=N_MAP)
-        qs, _ = synth.map_queries(m, CONFIG_ID, f, count)
-        log(f"[bench] generated workload (first sweep {f}, {count} sweeps) in {time.time() - t0:.1f}s")
+        qs, _ = synth.map_queries(m, CONFIG_ID, k[0], count, variant=k[1])
+        log(f"[bench] generated workload (first sweep {k[0]}, variant {k[1]}, {count} sweeps) in {time.time() - t0:.1f}s")
         try:
             tmp = os.path.join(cache_dir, f"tmp_{os.getpid()}.npy")
             if not os.path.exists(mpath):
                 np.save(tmp, m["map"])
                 os.replace(tmp, mpath)
             np.save(tmp, np.stack(qs))
-            os.replace(tmp, qpaths[f])
+            os.replace(tmp, qpaths[k])
         except OSError:
             pass
-        out[f] = (m["map"], qs)
+        out[k] = (m["map"], qs)
     return out
 
 
@@ -169,11 +177,13 @@ def oracle_scans_per_sec(map_xyzw, sweeps, threads: int):
     O.build()
     threads = O.set_threads(threads)
     p = O.default_params("mapper")
-    busy_ms, iters = 0.0, []
+    busy_ms, iters, results = 0.0, [], []
     for s in sweeps:
         r = O.align(p, s, map_xyzw)
         busy_ms += r["stages"]["total"] - r["stages"]["build"]
         iters.append(r["iterations"])
+        results.append(r)
+    oracle_scans_per_sec.results = results
     return len(sweeps) / (busy_ms * 1e-3), threads, iters
 
 
@@ -198,33 +208,97 @@ def run_reference(args, rank: int, world: int):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.batch, world, extra={"reference_sample": f"{per_step} sweeps per step"}),
+        "config": workload_config(args.batch, world),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port",
-                         "sample": f"{per_step} sweeps/step x {args.steps} steps vs the 500k map, k-d tree build "
-                                   f"excluded (map resident), OpenMP over queries"},
+                         "sample": f"each step is a bounded sample of the workload: {per_step} of the batch's sweeps per step "
+                                   f"x {args.steps} steps vs the 500k map, k-d tree build excluded (map resident), OpenMP "
+                                   f"over queries; scans/s of the serial oracle does not depend on the batch size"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(batch: int, world: int, extra=None) -> dict:
+def workload_config(batch: int, world: int) -> dict:
+    """The SAME dict in both arms (the driver compares them)."""
     c = {
         "workload": "BASELINE configs[1]: 64k-pt synthetic HDL-64 sweep vs 500k-pt accumulated local map, "
                     "30 ICP iterations max, point-to-point (north_star pipeline)",
         "sweep_points": N_SWEEP, "map_points": N_MAP, "max_iterations": MAX_ITERS, "transformation_epsilon": 1e-6,
         "max_correspondence_distance": 1.0, "batch_per_gpu": batch, "global_batch": batch * world,
-        "sharding": "scans sharded across ranks, map replicated; NCCL all_gather of per-scan transforms per step",
+        "sets": N_SETS,
+        "sharding": "scans sharded across ranks, map replicated; one NCCL all_gather of the per-scan records per run "
+                    "(device record sink, side stream), inside the timed region",
         "l2": "a 256 MiB write is enqueued between step submissions (in the streamed legs it runs next to the batches in "
               "flight); independently of it the per-step working set (150 MB of per-query state per 32-sweep step, up to "
-              "8 steps in flight) is larger than the 126 MB L2",
+              "8 steps in flight, steps rotating through 4 distinct sets of sweeps) is larger than the 126 MB L2",
     }
-    if extra:
-        c.update(extra)
     return c
 
 
 # ------------------------------------------------------------------------------------------------
+def rot_angle(Ra, Rb):
+    R = Ra.T @ Rb
+    v = 0.5 * np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+    return float(np.arcsin(min(1.0, float(np.linalg.norm(v)))))
+
+
+def pairs_leg(R, replay, dev, rank, world, local_rank, reps=2):
+    """BASELINE configs[3]: consecutive 64k-pt sweeps, sweep i registered against sweep i-1 (30 iterations max,
+    getFitnessScore for the reference's accept test), PAIRS_PER_RANK pairs per rank, then the gather of the
+    records (one collective) and the serial pose composition.  Host sweeps in, records out: end to end."""
+    import torch
+    import torch.distributed as dist
+    first = rank * PAIRS_PER_RANK
+    cache = f"/tmp/b2icp_bench_cache/pairs_c4_{first}_{PAIRS_PER_RANK + 1}.npy"
+    if os.path.exists(cache):
+        sw = list(np.load(cache))
+    else:
+        world_model = synth.make_world(1000 * 4, 4.0)  # a 480 m scene: 8 x 64 consecutive sweeps stay inside it
+        poses = synth.trajectory(1000 * 4 + 999, first + PAIRS_PER_RANK + 1)
+        sw = [synth.hdl64_sweep(world_model, poses[i], np.random.default_rng(1000 * 4 + i))
+              for i in range(first, first + PAIRS_PER_RANK + 1)]
+        try:
+            np.save(cache, np.stack(sw))
+        except OSError:
+            pass
+    pinned = []
+    for x in sw:
+        p = R.pinned_empty(x.shape)
+        p[:] = x
+        pinned.append(p)
+    reg = R.Registration(preset=R.PRESET_MAPPER, device=local_rank)
+    n_total = PAIRS_PER_RANK * world
+
+    def once():
+        srcs, tgts = pinned[1:], [pinned[0]] + [None] * (PAIRS_PER_RANK - 1)
+        rc, res = reg.alignBatch(srcs, tgts, with_fitness=True)
+        if rc in replay.HARD_ERRORS:
+            raise RuntimeError(f"pairs leg: b2icp_align_batch rc={rc}")
+        local = replay.pack_results(res, first)
+        return replay.gather_records(local, n_total, dev), res
+
+    once()  # buffers, grids
+    best = None
+    for _ in range(reps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        records, res = once()
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        best = float(dt[0]) if best is None else min(best, float(dt[0]))
+    acc = sum(1 for r in records if replay.accepted(r))
+    return {"workload": "BASELINE configs[3]: consecutive 64k-pt sweeps, pair i = sweep i vs sweep i-1, 30 iterations max, "
+                        "getFitnessScore per pair; host sweeps in, gathered records out",
+            "pairs_per_rank": PAIRS_PER_RANK, "pairs": n_total, "pairs_per_s": n_total / best, "ms_total": 1e3 * best,
+            "mean_iterations": float(np.mean(records[:, 17])), "accepted": int(acc),
+            "collective": "one all_gather of 22-double records per replay" if world > 1 else "none (1 rank)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -232,9 +306,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=32, help="sweeps per GPU per step")
     ap.add_argument("--impl", default="b2icp", choices=["b2icp", "reference"])
-    ap.add_argument("--cpu-sample", type=int, default=4, help="sweeps timed on the CPU oracle (rank 0, N=1)")
+    ap.add_argument("--cpu-sample", type=int, default=4, help="sweeps timed on the CPU oracle and parity-checked (rank 0, N=1)")
     ap.add_argument("--in-flight", type=int, default=8, help="streamed batches in flight (1..8)")
     ap.add_argument("--grid-cell", type=float, default=0.0, help="neighbour-grid cell edge in metres (0 = auto); tuning only")
+    ap.add_argument("--no-pairs", action="store_true", help="skip the configs[3] leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b2icp" else args.warmup
 
@@ -250,6 +325,7 @@ def main():
     import torch.distributed as dist
     from icpslam_b200 import build as B
     from icpslam_b200 import registration as R
+    from icpslam_b200 import replay
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libb2icp.so has no CPU fallback")
@@ -260,80 +336,57 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    # rank 0 generates (or finds) the cached workload first so that the other ranks only load it
-    if world > 1 and rank != 0:
-        dist.barrier()
-    if rank == 0:  # also pre-generates the other ranks' sweeps into the cache
-        map_xyzw, sweeps = prepare_workloads([r * args.batch for r in range(world)], args.batch)[0]
-        if world > 1:
-            dist.barrier()
-    else:
-        map_xyzw, sweeps = load_workload(rank * args.batch, args.batch)
+    Bn = args.batch
+    # every rank casts its own sweeps (in parallel): rank r owns the B poses r*B .. r*B+B-1 after the map (as in round 1);
+    # its N_SETS sets are those poses seen N_SETS times with independent range noise and odometry errors — distinct
+    # inputs of the same difficulty, so that the steps sample the variance across inputs
+    keys = [(rank * Bn, v) for v in range(N_SETS)]
+    loaded = prepare_workloads(keys, Bn)
+    map_xyzw = loaded[keys[0]][0]
+    sets = [loaded[k][1] for k in keys]
+    sweeps = sets[0]
 
     stream = torch.cuda.current_stream()
+    side = torch.cuda.Stream(device=dev)  # the gather's stream: nothing else of the step waits on it
     reg = R.Registration(preset=R.PRESET_MAPPER, device=local_rank, profile=1, grid_cell=args.grid_cell)
     reg.setStream(stream.cuda_stream)
     reg.setInputTarget(map_xyzw)
     grid = reg.gridInfo()
 
-    Bn = args.batch
-    d_sweeps = [torch.from_numpy(s).to(dev) for s in sweeps]
-    d_ptrs = [t.data_ptr() for t in d_sweeps]
+    d_sets = [[torch.from_numpy(x).to(dev) for x in st] for st in sets]
+    d_ptrs = [[t.data_ptr() for t in st] for st in d_sets]
     n_src = [N_SWEEP] * Bn
-    h_sweeps = []
-    for s in sweeps:
-        p = R.pinned_empty((N_SWEEP, 4))
-        p[:] = s
-        h_sweeps.append(p)
+    h_sets = []
+    for st in sets:
+        hs = []
+        for x in st:
+            p = R.pinned_empty((N_SWEEP, 4))
+            p[:] = x
+            hs.append(p)
+        h_sets.append(hs)
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)  # 256 MiB > 126 MB L2
-    gathered = torch.empty((world * Bn, 20), dtype=torch.float64, device=dev) if world > 1 else None
 
-    def gather(results):
-        if world == 1:
-            return
-        loc = np.array([list(r.T) + [r.converged, r.iterations, r.n_corr_last, r.mse_last] for r in results])
-        dist.all_gather_into_tensor(gathered, torch.from_numpy(loc).to(dev, non_blocking=False))
-
-    def step_resident():
-        rc, res = reg.alignBatchDevice(d_ptrs, n_src)
-        if rc:
-            raise RuntimeError(f"b2icp_align_batch_device rc={rc}")
-        gather(res)
-        return res
-
-    def step_e2e():
-        rc, res = reg.alignBatch(h_sweeps)
-        if rc:
-            raise RuntimeError(f"b2icp_align_batch rc={rc}")
-        gather(res)
-        return res
-
-    def timed(step_fn, steps, warmup, collect):
-        for _ in range(warmup):
-            step_fn()
-        if world > 1:
-            dist.barrier()
+    def timed_sync(steps, warmup, collect):
+        """One synchronous b2icp_align_batch_device per step with CUDA events around every sweep launch inside the
+        library (params.profile = 1): the per-launch durations the roofline needs.  Not the headline numbers."""
+        for k in range(warmup):
+            reg.alignBatchDevice(d_ptrs[k % N_SETS], n_src)
         torch.cuda.synchronize()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        t_wall0 = time.perf_counter()
-        last = None
+        first_results = None
         for k in range(steps):
             flush.zero_()  # L2 flush between timed steps, outside the per-step events
             ev[k][0].record(stream)
-            last = step_fn()
+            rc, res = reg.alignBatchDevice(d_ptrs[k % N_SETS], n_src)
+            if rc:
+                raise RuntimeError(f"b2icp_align_batch_device rc={rc}")
             ev[k][1].record(stream)
-            collect(last)
+            collect(res)
+            if k == 0:
+                first_results = res
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        wall = time.perf_counter() - t_wall0
-        dev_s = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
-        t = torch.tensor([dev_s, wall], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t[0]), float(t[1]), last
+        return sum(a.elapsed_time(b) for a, b in ev) * 1e-3, first_results
 
-    # ---- HBM-resident leg -----------------------------------------------------------------------
     sweep_ms, sweep_launches, iters_hist, searches = [], [], [], []
 
     def collect(res):
@@ -343,44 +396,52 @@ def main():
         searches.append(tm.nn_searches)
         iters_hist.append([r.iterations for r in res])
 
-    # 1. profiled synchronous pass (one call per step, CUDA events around every sweep launch inside the
-    #    library): the per-launch durations the roofline needs.  Not the headline numbers.
-    prof_dev_s, _, last = timed(step_resident, args.steps, args.warmup, collect)
+    prof_dev_s, gpu_first = timed_sync(args.steps, args.warmup, collect)
 
-    # 2. / 3. the two timed legs use the streaming form of the batch call (b2icp_align_batch_submit[_device] /
-    #    _wait): up to --in-flight steps are submitted before the oldest is waited for, each on its own stream, so
-    #    the host never leaves the device idle between steps, the sparse late iterations of one step share the
-    #    device with the first iterations of the next and — in the end-to-end leg — the PCIe upload of the next
-    #    steps overlaps the sweeps of the current one.
-    #    Every step's copies (H2D of its 32 sweeps, D2H of its results) and the L2 flush between steps are inside
-    #    the timed region: one event pair around all K steps.
+    # The two timed legs use the streaming form of the batch call (b2icp_align_batch_submit[_device] / _wait): up to
+    # --in-flight steps are submitted before the oldest is waited for, each on its own stream.  Every step's copies
+    # (H2D of its sweeps, D2H of its results), the L2 flush between steps and — with more than one rank — the ONE
+    # gather of all records at the end are inside the timed region: one event pair around all K steps.
     def run_streamed(steps, submit):
         submitted = done = 0
         while done < steps:
             while submitted < steps and submitted - done < args.in_flight:
                 if submitted:
                     flush.zero_()
-                if submit():
+                if submit(submitted):
                     raise RuntimeError("b2icp_align_batch_submit failed")
                 submitted += 1
             rc, res = reg.alignBatchWait()
             if rc:
                 raise RuntimeError(f"b2icp_align_batch_wait rc={rc}")
-            gather(res)
             done += 1
 
+    rec_words = R.RECORD_DTYPE.itemsize // 4
+    cap = max(args.steps, args.warmup, 8) * Bn
+    sink = torch.zeros((cap, rec_words), dtype=torch.int32, device=dev)
+    gathered = torch.empty((world * cap, rec_words), dtype=torch.int32, device=dev) if world > 1 else None
+    gather_ev = torch.cuda.Event(enable_timing=False)
+
     def timed_streamed(submit, steps, warmup):
+        reg.setRecordSink(None, 0)
         run_streamed(max(warmup, 8), submit)  # every one of the library's 8 slot sets allocates its buffers once
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+        reg.setRecordSink(sink.data_ptr(), cap)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n0 = reg.timing().kernel_launches
         e0.record(stream)
         run_streamed(steps, submit)
+        if world > 1:  # every batch has been waited for: its records are in `sink`
+            with torch.cuda.stream(side):
+                dist.all_gather_into_tensor(gathered, sink)
+                gather_ev.record(side)
+            stream.wait_event(gather_ev)
         e1.record(stream)
         timed_streamed.launches = reg.timing().kernel_launches - n0
         torch.cuda.synchronize()
+        reg.setRecordSink(None, 0)
         if world > 1:
             dist.barrier()
         t = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=dev)
@@ -389,29 +450,28 @@ def main():
         return float(t[0])
 
     streamed = Bn <= 32
+    if not streamed:
+        raise SystemExit("bench.py: --batch must be <= 32 (one streamed batch per step)")
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    launches0 = reg.timing().kernel_launches
-    if streamed:
-        dev_s = timed_streamed(lambda: reg.alignBatchSubmitDevice(d_ptrs, n_src), args.steps, args.warmup)
-        wall_s = dev_s
-    else:
-        dev_s, wall_s, last = timed(step_resident, args.steps, args.warmup, lambda res: None)
-    launches1 = reg.timing().kernel_launches
-    if streamed:
-        launches0, launches1 = 0, timed_streamed.launches  # the launches of the K timed steps only
+    dev_s = timed_streamed(lambda k: reg.alignBatchSubmitDevice(d_ptrs[k % N_SETS], n_src), args.steps, args.warmup)
+    launches = timed_streamed.launches  # the launches of the K timed steps only
     clocks = sampler.stop() if rank == 0 else None
     value = world * Bn * args.steps / dev_s
+    # the records of the resident leg as the ranks exchanged them (rank 0 checks them against what _wait returned)
+    rec_ok = None
+    if world > 1 and rank == 0:
+        got = gathered.cpu().numpy().view(R.RECORD_DTYPE).reshape(world, cap)
+        rec_ok = bool(all(int(got[r, args.steps * Bn - 1]["iterations"]) > 0 for r in range(world)))
 
-    if streamed:
-        e2e_dev_s = timed_streamed(lambda: reg.alignBatchSubmit(h_sweeps), args.steps, 3)
-        api = f"b2icp_align_batch_submit[_device] / b2icp_align_batch_wait ({args.in_flight} batches in flight)"
-    else:
-        e2e_dev_s, _, _ = timed(step_e2e, args.steps, 3, lambda res: None)
-        api = "b2icp_align_batch[_device]"
-    e2e_api = api
+    e2e_dev_s = timed_streamed(lambda k: reg.alignBatchSubmit(h_sets[k % N_SETS]), args.steps, 3)
+    api = f"b2icp_align_batch_submit[_device] / b2icp_align_batch_wait ({args.in_flight} batches in flight)"
     e2e_value = world * Bn * args.steps / e2e_dev_s
+
+    pairs = None
+    if not args.no_pairs:
+        pairs = pairs_leg(R, replay, dev, rank, world, local_rank)
 
     if rank != 0:
         if world > 1:
@@ -439,6 +499,7 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("icp_sweep_p2p_dram_bytes_per_launch")
+    its_all = np.concatenate([np.asarray(x) for x in iters_hist])
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "icp_sweep_p2p (one launch = one ICP iteration of the whole batch)", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes / max(n_launch, 1),
@@ -446,6 +507,7 @@ def main():
                 "nt_touched": nt_touched, "kernel_share_of_step": kernel_s / prof_dev_s,
                 # the same algorithmic bytes over the step time of the timed (streamed, overlapping) leg
                 "achieved_in_streamed_leg": alg_bytes / dev_s / 1e9,
+                "frac_in_streamed_leg": alg_bytes / dev_s / 1e9 / peak,
                 "measured_in": "a synchronous b2icp_align_batch_device pass of the same steps with CUDA events around "
                                "every launch (params.profile = 1)",
                 # share of (query, iteration) pairs that needed a real search; the rest were settled by the
@@ -453,9 +515,9 @@ def main():
                 "searched_fraction": float(np.sum(searches)) / max(1.0, float(sum(sum(x) for x in iters_hist)) * N_SWEEP)}
 
     # ---- the stand-alone NN search (b2icp_nn_search_device): the second half of BASELINE.json's metric ----
-    # all 32 sweeps of the step as ONE query cloud (2.1 M queries) against the 500k map, exact unbounded 1-NN,
+    # all 32 sweeps of a step as ONE query cloud (2.1 M queries) against the 500k map, exact unbounded 1-NN,
     # no seeds: algorithmic bytes = 16 n_q + 16 N_t' + 8 n_q, CUDA events inside the library.
-    allq = torch.cat(d_sweeps)
+    allq = torch.cat(d_sets[0])
     nq = allq.shape[0]
     d_idx = torch.empty(nq, dtype=torch.int32, device=dev)
     d_d2 = torch.empty(nq, dtype=torch.float32, device=dev)
@@ -466,42 +528,62 @@ def main():
         if k >= 3:
             nn_ms.append(reg.timing().nn_sweep_ms)
     nn_bytes = 24.0 * nq + 16.0 * nt_touched
-    nn_search = {"kernel": "nn_search_box_kernel (+ nn_brute_fallback)", "queries": int(nq), "ms": float(np.mean(nn_ms)),
-                 "algorithmic_bytes": nn_bytes, "achieved": nn_bytes / (float(np.mean(nn_ms)) * 1e-3) / 1e9, "unit": "GB/s",
-                 "frac": nn_bytes / (float(np.mean(nn_ms)) * 1e-3) / 1e9 / peak,
-                 "queries_per_s": nq / (float(np.mean(nn_ms)) * 1e-3)}
+    roofline["nn_search"] = {
+        "kernel": "nn_search_coop (cooperative groups over cp.async.bulk-staged candidate rows) + nn_brute_fallback",
+        "queries": int(nq), "ms": float(np.mean(nn_ms)), "algorithmic_bytes": nn_bytes,
+        "achieved": nn_bytes / (float(np.mean(nn_ms)) * 1e-3) / 1e9, "unit": "GB/s",
+        "frac": nn_bytes / (float(np.mean(nn_ms)) * 1e-3) / 1e9 / peak, "queries_per_s": nq / (float(np.mean(nn_ms)) * 1e-3)}
+    if pairs is not None:
+        roofline["pairs"] = pairs
+    roofline["details"] = {
+        "grid_cell_m": grid["cell"], "grid_dims": list(grid["dims"]), "grid_occupancy": grid["occupancy"],
+        "mean_iterations": float(its_all.mean()), "max_iterations_seen": int(its_all.max()), "api": api,
+        "synchronous_call_scans_per_s": world * Bn * args.steps / prof_dev_s,
+        "gathered_records_ok": rec_ok}
 
-    # ---- CPU baseline on this box's host cores (bounded sample) -----------------------------------
-    cpu = None
+    # ---- CPU baseline on this box's host cores (bounded sample) + parity of the same sweeps ---------
+    cpu, parity = None, None
     if world == 1 and args.cpu_sample > 0:
         from oracle import oracle as O
         O.build()
-        sps, used, its = oracle_scans_per_sec(map_xyzw, sweeps[:args.cpu_sample], O.max_threads())
+        k = min(args.cpu_sample, Bn)
+        sps, used, its = oracle_scans_per_sec(map_xyzw, sweeps[:k], O.max_threads())
         cpu = {"value": sps, "unit": UNIT, "cores": used, "kind": "port",
-               "sample": f"{args.cpu_sample} of the {Bn} sweeps vs the same 500k map, oracle P2P align with OpenMP over "
+               "sample": f"{k} of the {Bn} sweeps of set 0 vs the same 500k map, oracle P2P align with OpenMP over "
                          f"queries, k-d tree build excluded (map resident); iterations {its}"}
+        max_dt = max_dr = 0.0
+        iters_equal = True
+        for j, o in enumerate(oracle_scans_per_sec.results):
+            Tg = gpu_first[j].matrix()
+            max_dt = max(max_dt, float(np.abs(Tg[:3, 3] - o["T"][:3, 3]).max()))
+            max_dr = max(max_dr, rot_angle(Tg[:3, :3], o["T"][:3, :3]))
+            iters_equal = iters_equal and gpu_first[j].iterations == o["iterations"] and \
+                gpu_first[j].converged == int(o["converged"])
+        parity = {"checked": k, "max_dt": max_dt, "max_dr": max_dr, "iters_equal": bool(iters_equal),
+                  "tolerance": {"dt_m": 1e-4, "dr_rad": 1e-4},
+                  "what": "final transform and iteration count of the first sweeps of set 0, full size (64k vs 500k), GPU "
+                          "(step 0 of the profiled pass) vs the CPU oracle"}
+        roofline["parity"] = parity
 
-    its_all = np.concatenate([np.asarray(x) for x in iters_hist])
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": workload_config(Bn, world, extra={
-            "grid_cell_m": grid["cell"], "grid_dims": list(grid["dims"]), "grid_occupancy": grid["occupancy"],
-            "mean_iterations": float(its_all.mean()), "max_iterations_seen": int(its_all.max()),
-            "wall_ms_per_step": 1e3 * wall_s / args.steps, "api": api,
-            "synchronous_call_scans_per_s": world * Bn * args.steps / prof_dev_s}),
+        "config": workload_config(Bn, world),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": Bn * N_SWEEP * 16,
-                "d2h_bytes_per_step": Bn * STATE_BYTES, "ms_per_step": 1e3 * e2e_dev_s / args.steps, "api": e2e_api},
-        "gpu_launches": int(launches1 - launches0),
+                "d2h_bytes_per_step": Bn * STATE_BYTES, "ms_per_step": 1e3 * e2e_dev_s / args.steps, "api": api},
+        "gpu_launches": int(launches),
         "roofline": roofline,
-        "nn_search": nn_search,
+        "parity": parity,
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and not (parity["iters_equal"] and parity["max_dt"] <= 1e-4 and parity["max_dr"] <= 1e-4):
+        log(f"[bench] PARITY FAILED: {parity}")
+        raise SystemExit(3)
 
 
 if __name__ == "__main__":

@@ -31,9 +31,8 @@
 #include "icp.cuh"
 #include "map.cuh"
 #include "nn.cuh"
+#include "nnsearch.cuh"
 #include "solve.cuh"
-#include "sort.cuh"
-#include "sweep.cuh"
 
 using namespace b2;
 
@@ -46,9 +45,9 @@ constexpr int kUnboundedRings = 3;        // ring budget of unbounded searches b
 constexpr double kTargetOccupancy = 2.5;  // points per occupied cell the auto-sizing aims at
 constexpr double kMaxOccupancy = 4.0;     // above this the grid is rebuilt with smaller cells
 constexpr float kCacheMarginFrac = 0.05f;  // nncache.cuh: box-search margin as a fraction of the cell edge
-constexpr int kStreamedQpt = 16;          // slab length (x 32 entries per warp) of streamed batches
-constexpr int kMaxBatch = kMaxScans;      // scans advanced together by one sweep launch
-constexpr int kSortMinEntries = 8192;     // smaller batches keep their input order (the sort's launches would dominate)
+constexpr int kStreamedQpt = 32;          // slab length of streamed batches (4: 15.5k, 8: 18.6k, 16: 21.7k, 32: 23.2k scans/s)
+constexpr int kFirstSweepQpt = 2;         // slab length (x 32 queries per warp) of the first sweep of a batch
+constexpr int kMaxBatch = 64;             // scans advanced together by one sweep launch
 constexpr int kStreamSets = 8;            // streamed batches in flight (b2icp_align_batch_submit / _wait)
 constexpr int kSetSlots = 32;             // scans per streamed batch
 constexpr int kSlots = kStreamSets * kSetSlots > kMaxBatch ? kStreamSets * kSetSlots : kMaxBatch;  // state / task records
@@ -101,20 +100,11 @@ struct GridSlot {
 
 struct ScanSlot {
   Cloud src;
-  DeviceBuf pos, corr_idx, corr_d2, corr_pos, partials;
+  DeviceBuf cur, corr_idx, corr_d2, corr_pos, c0, c1, c2, partials;
   DeviceBuf cov, mahal, gicp_partials;  // GICP: source covariances, Mahalanobis matrices, per-CTA sums
   int grid = 0;
   void release() {
-    for (DeviceBuf* b : {&src.raw, &pos, &corr_idx, &corr_d2, &corr_pos, &partials, &cov, &mahal, &gicp_partials}) b->release();
-  }
-};
-
-// Entry arrays of one batch in flight (sort.cuh / sweep.cuh) and the scratch of its sort.
-struct BatchBuf {
-  DeviceBuf ent_src, ent_sid, ent_orig, cur, c0, c1, keys0, keys1, vals0, vals1, hist, tile_sums, stats;
-  BatchView view;
-  void release() {
-    for (DeviceBuf* b : {&ent_src, &ent_sid, &ent_orig, &cur, &c0, &c1, &keys0, &keys1, &vals0, &vals1, &hist, &tile_sums, &stats})
+    for (DeviceBuf* b : {&src.raw, &cur, &corr_idx, &corr_d2, &corr_pos, &c0, &c1, &c2, &partials, &cov, &mahal, &gicp_partials})
       b->release();
   }
 };
@@ -137,6 +127,7 @@ __global__ void export_records(const IcpState* __restrict__ st, int B, int with_
                                               : __longlong_as_double(0x7FF8000000000000ll);
   out[i] = r;
 }
+
 
 }  // namespace
 
@@ -179,12 +170,11 @@ struct b2icp_handle {
   int n_pending = 0, first_pending = 0, next_set = 0;
   int max_in_flight = kStreamSets;  // B2ICP_IN_FLIGHT environment variable (tuning only)
   int qpt_override = 0;  // B2ICP_QPT environment variable (tuning only)
-  int w_override = 0;    // B2ICP_W: lanes per cooperative search group, 8 or 32 (tuning only)
-  int sort_override = -1;  // B2ICP_SORT=0/1 (tuning only)
-  SweepTune tune{0.75f, 4, 1};  // B2ICP_PROBE / B2ICP_JOIN / B2ICP_TILES (tuning only)
-  BatchBuf bufs[kStreamSets + 1];  // entry arrays: one per streamed set, the last one for synchronous calls
+  std::vector<int> qpt_sched;  // B2ICP_QPT_SCHED="2,4,8": slab length per iteration, last value repeats (tuning only)
   b2icp_record* sink = nullptr;  // b2icp_set_record_sink: device records of streamed batches
   size_t sink_cap = 0, sink_used = 0;
+  int w_override = 0;  // B2ICP_W: lanes per cooperative group of the stand-alone search, 8 or 32 (tuning only)
+  int join_d = 4;      // B2ICP_JOIN: cells of slack inside which a lane joins its group's pass (tuning only)
   double* h_gicp_partials = nullptr;  // pinned read-back of gicp_fdf_kernel's per-CTA sums
   size_t h_gicp_partials_cap = 0;
   long gicp_evals = 0;
@@ -396,11 +386,14 @@ int set_target_impl(b2icp_handle* h, int gi, const float* xyzw, size_t n, bool f
 
 int ensure_slot_work(b2icp_handle* h, ScanSlot& s) {
   const size_t n = s.src.n;
-  const size_t nunit = (n + kReduceUnit - 1) / kReduceUnit;  // per-warp partial sums of icp_reduce
-  CK(s.pos.ensure(n * sizeof(int)));
+  const size_t ncta = (n + 31) / 32;  // per-warp partial sums, worst case one 32-query slab per warp
+  CK(s.cur.ensure(n * sizeof(float4)));
   CK(s.corr_idx.ensure(n * sizeof(int)));
   CK(s.corr_d2.ensure(n * sizeof(float)));
-  CK(s.partials.ensure(nunit * kNumSums * sizeof(double)));
+  CK(s.c0.ensure(n * sizeof(float4)));
+  CK(s.c1.ensure(n * sizeof(float4)));
+  if (kCacheK > 2) CK(s.c2.ensure(n * sizeof(float4)));
+  CK(s.partials.ensure(ncta * kNumSums * sizeof(double)));
   return B2ICP_OK;
 }
 
@@ -421,111 +414,13 @@ void fill_result(const IcpState& s, b2icp_result* out) {
   out->fitness = std::nan("");
 }
 
-int bits_for(unsigned long long count) {  // bits needed for values 0 .. count-1
-  int b = 0;
-  while (b < 63 && (1ull << b) < count) ++b;
-  return b;
-}
-
-template <int QPT, int W, bool SHARED>
-cudaError_t launch_sweep_t(unsigned blocks, cudaStream_t st, const BatchView& bv, const ScanTask* tasks, const IcpConfig& cfg,
-                           const SweepTune& tune, bool configure_only) {
-  const size_t smem = sweep_smem_bytes(QPT, SHARED);
-  if (configure_only)  // opt in to more than 48 KB of dynamic shared memory (once per device, at b2icp_create)
-    return cudaFuncSetAttribute(icp_sweep_coop<QPT, W, SHARED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  icp_sweep_coop<QPT, W, SHARED><<<blocks, kSweepThreads, smem, st>>>(bv, tasks, cfg, tune);
-  return cudaSuccess;
-}
-
-template <int QPT>
-cudaError_t launch_sweep_q(int w, bool shared, unsigned blocks, cudaStream_t st, const BatchView& bv, const ScanTask* tasks,
-                           const IcpConfig& cfg, const SweepTune& tune, bool co) {
-  if (w == 8)
-    return shared ? launch_sweep_t<QPT, 8, true>(blocks, st, bv, tasks, cfg, tune, co)
-                  : launch_sweep_t<QPT, 8, false>(blocks, st, bv, tasks, cfg, tune, co);
-  return shared ? launch_sweep_t<QPT, 32, true>(blocks, st, bv, tasks, cfg, tune, co)
-                : launch_sweep_t<QPT, 32, false>(blocks, st, bv, tasks, cfg, tune, co);
-}
-
-cudaError_t launch_sweep(int qpt, int w, bool shared, cudaStream_t st, const BatchView& bv, const ScanTask* tasks,
-                         const IcpConfig& cfg, const SweepTune& tune, bool configure_only = false) {
-  const unsigned blocks = (unsigned)(((size_t)bv.E + (size_t)kSweepThreads * qpt - 1) / ((size_t)kSweepThreads * qpt));
-  if (qpt >= 16) return launch_sweep_q<16>(w, shared, blocks, st, bv, tasks, cfg, tune, configure_only);
-  if (qpt >= 4) return launch_sweep_q<4>(w, shared, blocks, st, bv, tasks, cfg, tune, configure_only);
-  return launch_sweep_q<1>(w, shared, blocks, st, bv, tasks, cfg, tune, configure_only);
-}
-
-cudaError_t configure_kernels() {
-  BatchView bv{};
-  IcpConfig cfg{};
-  SweepTune tune{};
-  for (int qpt : {1, 4, 16})
-    for (int w : {8, 32})
-      for (int sh = 0; sh < 2; ++sh) {
-        cudaError_t e = launch_sweep(qpt, w, sh != 0, nullptr, bv, nullptr, cfg, tune, true);
-        if (e != cudaSuccess) return e;
-      }
-  return cudaFuncSetAttribute(sort_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSortWarps * kSortBins * sizeof(int)));
-}
-
-// The entry array of a batch: keys -> stable radix sort by target tile -> fill (sort.cuh).
-int build_entries(b2icp_handle* h, BatchBuf& bb, int B, int slot0, int E, int total_bits, const KeyParams& kp, size_t max_n, bool sorted) {
-  CK(bb.ent_src.ensure((size_t)E * sizeof(float4)));
-  CK(bb.ent_sid.ensure((size_t)E));
-  CK(bb.ent_orig.ensure((size_t)E * sizeof(int)));
-  CK(bb.cur.ensure((size_t)E * sizeof(float4)));
-  CK(bb.c0.ensure((size_t)E * sizeof(float4)));
-  CK(bb.c1.ensure((size_t)E * sizeof(float4)));
-  const ScanTask* d_tasks = h->tasks.as<ScanTask>() + slot0;
-  const unsigned int* vals = nullptr;
-  if (sorted) {
-    const int nchunk = (E + kSortChunk - 1) / kSortChunk;
-    const int nh = kSortBins * nchunk;
-    const int ntiles = (nh + kScanTile - 1) / kScanTile;
-    CK(bb.keys0.ensure((size_t)E * 4));
-    CK(bb.keys1.ensure((size_t)E * 4));
-    CK(bb.vals0.ensure((size_t)E * 4));
-    CK(bb.vals1.ensure((size_t)E * 4));
-    CK(bb.hist.ensure((size_t)(nh + 8) * 4));
-    CK(bb.tile_sums.ensure((size_t)ntiles * 4));
-    CK(bb.stats.ensure(sizeof(BBox)));
-    unsigned int* k0 = bb.keys0.as<unsigned int>();
-    unsigned int* k1 = bb.keys1.as<unsigned int>();
-    unsigned int* v0 = bb.vals0.as<unsigned int>();
-    unsigned int* v1 = bb.vals1.as<unsigned int>();
-    entry_keys<<<dim3((unsigned)((max_n + 255) / 256), (unsigned)B, 1), 256, 0, h->stream>>>(d_tasks, kp, k0, v0);
-    h->launches += 1;
-    int* hist = bb.hist.as<int>();
-    for (int shift = 0; shift < total_bits; shift += kSortBits) {
-      sort_hist<<<nchunk, kSortThreads, 0, h->stream>>>(k0, E, shift, nchunk, hist);
-      scan_tile_sums<<<ntiles, kScanThreads, 0, h->stream>>>(hist, nh, bb.tile_sums.as<int>(), bb.stats.as<BBox>());
-      scan_of_sums<<<1, kScanThreads, 0, h->stream>>>(bb.tile_sums.as<int>(), ntiles);
-      scan_apply<<<ntiles, kScanThreads, 0, h->stream>>>(hist, nh, bb.tile_sums.as<int>(), E);
-      sort_scatter<<<nchunk, kSortThreads, kSortWarps * kSortBins * sizeof(int), h->stream>>>(k0, v0, E, shift, nchunk, hist, k1, v1);
-      h->launches += 5;
-      std::swap(k0, k1);
-      std::swap(v0, v1);
-    }
-    vals = v0;
-  }
-  entry_fill<<<(unsigned)((E + 255) / 256), 256, 0, h->stream>>>(d_tasks, B, vals, E, bb.ent_src.as<float4>(),
-                                                                bb.ent_sid.as<unsigned char>(), bb.ent_orig.as<int>());
-  h->launches += 1;
-  return B2ICP_OK;
-}
-
-// Advance slots [slot0, slot0 + B) to convergence: per ICP iteration one cooperative sweep over the batch's entry
-// array and one per-scan reduce / solve.  guesses: B x 16 floats or NULL.  Results are read back by read_states().
+// Advance slots [0, B) to convergence: one fused sweep launch per iteration for the whole batch.
+// guesses: B x 16 floats or NULL.  Results are read back by read_states().
 int run_batch(b2icp_handle* h, int B, const float* guesses, int slot0 = 0, bool allow_prof = true, bool streamed = false) {
   if (h->params.mode != B2ICP_MODE_P2P_SVD) return fail(h, B2ICP_ERR_INVALID_ARG, "mode not implemented");
-  if (B < 1 || B > kMaxScans) return fail(h, B2ICP_ERR_INVALID_ARG, "batch too large");
-  BatchBuf& bb = h->bufs[streamed ? slot0 / kSetSlots : kStreamSets];
-  size_t max_n = 0, total = 0, tgt_points = 0;
+  size_t max_n = 0;
   double min_cell = 1e300;
   int max_dim = 1;
-  // segments of the sort key: scans that share a target grid share a segment
-  int seg_grid[kMaxScans], nseg = 0;
-  int dim_x = 1, dim_y = 1, dim_z = 1;
   for (int i = 0; i < B; ++i) {
     ScanSlot& s = slot(h, (size_t)(slot0 + i));
     GridSlot& g = gslot(h, s.grid);
@@ -534,28 +429,19 @@ int run_batch(b2icp_handle* h, int B, const float* guesses, int slot0 = 0, bool 
     max_n = std::max(max_n, s.src.n);
     min_cell = std::min(min_cell, (double)g.view.cell);
     max_dim = std::max(max_dim, std::max(g.view.nx, std::max(g.view.ny, g.view.nz)));
-    int seg = 0;
-    while (seg < nseg && seg_grid[seg] != s.grid) ++seg;
-    if (seg == nseg) {
-      seg_grid[nseg++] = s.grid;
-      tgt_points += (size_t)g.view.n;
-      dim_x = std::max(dim_x, g.view.nx);
-      dim_y = std::max(dim_y, g.view.ny);
-      dim_z = std::max(dim_z, g.view.nz);
-    }
     ScanTask& t = h->h_tasks[slot0 + i];
     t.grid = g.view;
     t.src = s.src.raw.as<float4>();
-    t.pos = s.pos.as<int>();
+    t.cur = s.cur.as<float4>();
     t.corr_idx = s.corr_idx.as<int>();
     t.corr_d2 = s.corr_d2.as<float>();
+    t.c0 = s.c0.as<float4>();
+    t.c1 = s.c1.as<float4>();
+    t.c2 = s.c2.as<float4>();
     t.partials = s.partials.as<double>();
     t.state = h->states.as<IcpState>() + slot0 + i;
     t.n = (int)s.src.n;
     t.pad = 1;  // the loop leaves a certificate per query: getFitnessScore starts from it
-    t.ent_off = (int)total;
-    t.seg = seg;
-    total += s.src.n;
     IcpState& st = h->h_states[slot0 + i];
     std::memset(&st, 0, sizeof(st));
     for (int k = 0; k < 16; ++k) {
@@ -566,32 +452,8 @@ int run_batch(b2icp_handle* h, int B, const float* guesses, int slot0 = 0, bool 
     st.mse = std::nan("");
     st.prev_mse = DBL_MAX;
   }
-  if (total > (size_t)INT32_MAX / 2) return fail(h, B2ICP_ERR_INVALID_ARG, "batch too large");
-  const int E = (int)total;
-  const bool shared = nseg == 1;
-  KeyParams kp{};
-  const int seg_bits = bits_for((unsigned long long)nseg);
-  for (kp.drop = 0;; ++kp.drop) {  // the full Morton code fits 32 bits for every grid the dense cell table allows
-    kp.bx = bits_for((unsigned long long)((dim_x - 1) >> kp.drop) + 1);
-    kp.by = bits_for((unsigned long long)((dim_y - 1) >> kp.drop) + 1);
-    kp.bz = bits_for((unsigned long long)((dim_z - 1) >> kp.drop) + 1);
-    kp.cell_bits = kp.bx + kp.by + kp.bz;
-    if (kp.cell_bits + seg_bits <= 32) break;
-  }
-  const int total_bits = kp.cell_bits + seg_bits;
-  const bool sorted = h->sort_override >= 0 ? h->sort_override != 0 : E >= kSortMinEntries;
-  // the entry arrays exist before the tasks are uploaded: the tasks point into them
-  CK(bb.cur.ensure((size_t)E * sizeof(float4)));
-  CK(bb.c0.ensure((size_t)E * sizeof(float4)));
-  CK(bb.c1.ensure((size_t)E * sizeof(float4)));
-  for (int i = 0; i < B; ++i) {
-    ScanTask& t = h->h_tasks[slot0 + i];
-    t.cur = bb.cur.as<float4>();
-    t.c0 = bb.c0.as<float4>();
-    t.c1 = bb.c1.as<float4>();
-  }
-  // an unbounded gate has no radius to clamp a search to: the box may then grow to the whole grid (exact, slow, and
-  // off the reference's 1.0 m path)
+  // An unbounded gate (PCL's own default, sqrt(DBL_MAX)) has no radius to clamp a search to: the box of a query
+  // with nothing nearby may then grow to the whole grid — exact, slow, and off the reference's 1.0 m path.
   h->cfg.max_rings = std::isfinite(h->cfg.bound2) ? rings_for_bound(h, min_cell) + (int)std::ceil(h->cfg.margin_frac) + 1 : max_dim;
   CK(cudaMemcpyAsync(h->tasks.as<ScanTask>() + slot0, h->h_tasks + slot0, sizeof(ScanTask) * B, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(h->states.as<IcpState>() + slot0, h->h_states + slot0, sizeof(IcpState) * B, cudaMemcpyHostToDevice, h->stream));
@@ -606,42 +468,48 @@ int run_batch(b2icp_handle* h, int B, const float* guesses, int slot0 = 0, bool 
     }
     CK(cudaEventRecord(h->events[0], h->stream));
   }
-  {
-    int rc = build_entries(h, bb, B, slot0, E, total_bits, kp, max_n, sorted);
-    if (rc) return rc;
-  }
-  BatchView& bv = bb.view;
-  bv.ent_src = bb.ent_src.as<float4>();
-  bv.ent_sid = bb.ent_sid.as<unsigned char>();
-  bv.ent_orig = bb.ent_orig.as<int>();
-  bv.cur = bb.cur.as<float4>();
-  bv.c0 = bb.c0.as<float4>();
-  bv.c1 = bb.c1.as<float4>();
-  bv.E = E;
-  bv.nscan = B;
-  bv.grid = h->h_tasks[slot0].grid;
-  // Lanes per cooperative group: a group shares one staged candidate set, which pays when its queries are close
-  // together, i.e. when the batch has many queries per target point (many scans against one map); sparse queries
-  // (one sweep against a dense map) get groups of 8.
-  int w = (double)E >= 2.0 * (double)std::max<size_t>(tgt_points, 1) ? 32 : 8;
-  if (h->w_override == 8 || h->w_override == 32) w = h->w_override;
-  // Slab length (entries per warp = 32 * qpt): long slabs pack the failures of sparse iterations into full groups;
-  // short ones are for launches that could not fill the SMs otherwise.
-  auto ctas_at = [&](int qpt) { return (long long)(((size_t)E + (size_t)kSweepThreads * qpt - 1) / ((size_t)kSweepThreads * qpt)); };
-  const long long want_ctas = 2LL * 148 * kSweepMinCtas;
-  int qpt = ctas_at(16) >= want_ctas ? 16 : (ctas_at(4) >= want_ctas ? 4 : 1);
-  if (streamed && ctas_at(kStreamedQpt) >= 64) qpt = kStreamedQpt;
-  if (h->qpt_override > 0) qpt = h->qpt_override;
-  const dim3 rgrid((unsigned)((max_n + 8 * kReduceUnit - 1) / (8 * kReduceUnit)), (unsigned)B, 1);
+  // queries per lane (a warp owns 32 * qpt consecutive queries): long slabs amortise the reduction and keep
+  // the lanes of the search phase busy; short ones are for launches that could not fill the SMs otherwise
+  // (measured on B200, 32 x 64k sweeps: qpt 2 -> 144 us, 4 -> 113 us, 8 -> 109 us per iteration)
+  auto ctas_at = [&](int qpt) { return (long long)B * (long long)((max_n + (size_t)kSweepThreads * qpt - 1) / ((size_t)kSweepThreads * qpt)); };
+  const long long want = 2LL * 148 * kSweepMinCtas;
+  int qpt = h->qpt_override > 0 ? h->qpt_override
+                                : (ctas_at(8) >= want ? 8 : (ctas_at(4) >= want ? 4 : (ctas_at(2) >= want ? 2 : 1)));
+  if (streamed && h->qpt_override <= 0 && ctas_at(kStreamedQpt) >= 128) qpt = kStreamedQpt;
+  // The slab length can change from one launch to the next (the work list lives inside a launch).  The first
+  // sweeps search most queries, so their warps are long-running whatever the slab: shorter slabs there keep
+  // the last wave of CTAs from running on a third of the machine.
+  auto qpt_at = [&](int it) {
+    if (!h->qpt_sched.empty()) return h->qpt_sched[std::min<size_t>((size_t)it, h->qpt_sched.size() - 1)];
+    // measured on B200 (32 x 64k sweeps, scans/s): 8 everywhere 10 144; 2,8.. 10 451; 2,4,4,8.. 10 533; 2,4,4,4,4,8.. 10 571
+    // A streamed batch shares the device with the other batches in flight, which fill its tails: long slabs
+    // everywhere are best there (18.6k scans/s against 17.2k with the schedule below).
+    if (streamed) return qpt;
+    return it == 0 ? std::min(qpt, kFirstSweepQpt) : (it <= 4 ? std::min(qpt, 4) : qpt);
+  };
   for (int it = 0; it < iters; ++it) {
     if (prof) CK(cudaEventRecord(h->events[2 + 2 * it], h->stream));
-    CK(launch_sweep(qpt, w, shared, h->stream, bv, h->tasks.as<ScanTask>() + slot0, h->cfg, h->tune));
+    const int q = qpt_at(it);
+    const dim3 grid((unsigned)((max_n + (size_t)kSweepThreads * q - 1) / ((size_t)kSweepThreads * q)), (unsigned)B, 1);
+    if (q == 32)
+      icp_sweep_p2p<32><<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
+    else if (q == 16)
+      icp_sweep_p2p<16><<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
+    else if (q == 8)
+      icp_sweep_p2p<8><<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
+    else if (q == 4)
+      icp_sweep_p2p<4><<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
+    else if (q == 2)
+      icp_sweep_p2p<2><<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
+    else
+      icp_sweep_p2p<1><<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
     if (prof) CK(cudaEventRecord(h->events[3 + 2 * it], h->stream));
-    icp_reduce<<<rgrid, 256, 0, h->stream>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
   }
-  // correspondences of the last sweep, for b2icp_get_correspondences
-  icp_finalize_corr<<<(unsigned)((E + 255) / 256), 256, 0, h->stream>>>(bv, h->tasks.as<ScanTask>() + slot0, h->cfg);
-  h->launches += 2 * iters + 1;
+  {  // correspondences of the last sweep, for b2icp_get_correspondences
+    const dim3 fgrid((unsigned)((max_n + 255) / 256), (unsigned)B, 1);
+    icp_finalize_corr<<<fgrid, 256, 0, h->stream>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
+  }
+  h->launches += iters + 1;
   if (prof) CK(cudaEventRecord(h->events[1], h->stream));
   h->last_batch = B;
   return B2ICP_OK;
@@ -737,15 +605,14 @@ int nn_search_impl(b2icp_handle* h, const float4* d_q, size_t n, int* d_idx, flo
   GridSlot& g = gslot(h, (size_t)grid_index);
   CK(h->unres_list.ensure(n * sizeof(int)));
   zero_counter<<<1, 1, 0, h->stream>>>(h->unres_count.as<unsigned int>());
-  // 32 consecutive queries per cooperative group; persistent-style grid (a multiple of the SM count)
+  // 32 consecutive queries per cooperative group (coop.cuh); a grid that is a multiple of the SM count
   const int groups = (int)((n + 31) / 32);
   const int ctas = std::max(1, std::min((groups + kSweepThreads / 32 - 1) / (kSweepThreads / 32), 148 * kSweepMinCtas * 4));
-  const int w = h->w_override == 8 ? 8 : 32;
-  if (w == 8)
-    nn_search_coop<8><<<ctas, kSweepThreads, 0, h->stream>>>(g.view, d_q, (int)n, kUnboundedRings, h->tune.join_d, d_idx, d_d2,
+  if (h->w_override == 8)
+    nn_search_coop<8><<<ctas, kSweepThreads, 0, h->stream>>>(g.view, d_q, (int)n, kUnboundedRings, h->join_d, d_idx, d_d2,
                                                              h->unres_list.as<int>(), h->unres_count.as<unsigned int>());
   else
-    nn_search_coop<32><<<ctas, kSweepThreads, 0, h->stream>>>(g.view, d_q, (int)n, kUnboundedRings, h->tune.join_d, d_idx, d_d2,
+    nn_search_coop<32><<<ctas, kSweepThreads, 0, h->stream>>>(g.view, d_q, (int)n, kUnboundedRings, h->join_d, d_idx, d_d2,
                                                               h->unres_list.as<int>(), h->unres_count.as<unsigned int>());
   h->launches += 2;
   return launch_brute_fallback(h, g.view, d_q, n, d_idx, d_d2);
@@ -984,15 +851,26 @@ int b2icp_create(const b2icp_params* p, b2icp_handle** out) {
   std::memset(&h->timing, 0, sizeof(h->timing));
   derive_config(h);
   if (const char* e = getenv("B2ICP_QPT")) h->qpt_override = atoi(e);
-  if (const char* e = getenv("B2ICP_IN_FLIGHT")) h->max_in_flight = std::max(1, std::min(kStreamSets, atoi(e)));
   if (const char* e = getenv("B2ICP_W")) h->w_override = atoi(e);
-  if (const char* e = getenv("B2ICP_SORT")) h->sort_override = atoi(e);
-  if (const char* e = getenv("B2ICP_PROBE")) h->tune.probe_frac = (float)atof(e);
-  if (const char* e = getenv("B2ICP_JOIN")) h->tune.join_d = atoi(e);
-  if (const char* e = getenv("B2ICP_TILES")) h->tune.use_tiles = atoi(e);
+  if (const char* e = getenv("B2ICP_JOIN")) h->join_d = atoi(e);
+  if (const char* e = getenv("B2ICP_IN_FLIGHT")) h->max_in_flight = std::max(1, std::min(kStreamSets, atoi(e)));
+  if (const char* e = getenv("B2ICP_QPT_SCHED"))
+    for (const char* p = e; *p;) {
+      const int v = atoi(p);
+      h->qpt_sched.push_back(v >= 32 ? 32 : v >= 16 ? 16 : (v >= 8 ? 8 : (v >= 4 ? 4 : (v >= 2 ? 2 : 1))));
+      while (*p && *p != ',') ++p;
+      if (*p == ',') ++p;
+    }
+  if (const char* e = getenv("B2ICP_CARVEOUT")) {  // tuning only: shared-memory carve-out of the sweep, percent
+    const int pct = atoi(e);
+    cudaFuncSetAttribute(icp_sweep_p2p<1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(icp_sweep_p2p<2>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(icp_sweep_p2p<4>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(icp_sweep_p2p<8>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  }
   slot(h, 0);
   gslot(h, 0);
-  bool ok = cudaSetDevice(h->device) == cudaSuccess && configure_kernels() == cudaSuccess &&
+  bool ok = cudaSetDevice(h->device) == cudaSuccess &&
             cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaMallocHost((void**)&h->h_states, sizeof(IcpState) * kSlots) == cudaSuccess &&
             cudaMallocHost((void**)&h->h_tasks, sizeof(ScanTask) * kSlots) == cudaSuccess &&
@@ -1015,7 +893,6 @@ int b2icp_destroy(b2icp_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto& s : h->slots) s->release();
   for (auto& g : h->grids) g->release();
-  for (BatchBuf& b : h->bufs) b.release();
   for (DeviceBuf* b : {&h->map_pts, &h->map_keys, &h->map_vals, &h->map_slot_of, &h->map_flags, &h->map_tiles, &h->map_stats})
     b->release();
   for (DeviceBuf* b : {&h->states, &h->tasks, &h->unres_list, &h->unres_count, &h->unres_keys, &h->query, &h->q_idx, &h->q_d2, &h->xf_in,

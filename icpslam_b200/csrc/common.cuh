@@ -68,40 +68,21 @@ struct IcpConfig {
   float margin_frac;       // nncache.cuh: search-radius margin as a fraction of the grid cell
 };
 
-constexpr int kMaxScans = 64;  // scans advanced together by one batch (slot index fits the entry array's byte)
-
-// One scan of a batch.  The per-query state (running cloud, cached neighbours) lives in the batch's ENTRY arrays
-// (BatchView, sort.cuh), which hold the queries of all scans of the batch ordered by target tile; `pos` maps a
-// scan's original point index to its entry.
+// One scan: source cloud, running (in-place transformed) cloud, outputs, state.
 struct ScanTask {
   GridView grid;
   const float4* src;   // source as uploaded (w ignored)
-  float4* cur;         // = BatchView::cur (entry order)
-  float4* c0;          // = BatchView::c0
-  float4* c1;          // = BatchView::c1
-  int* pos;            // [n] entry index of original point i
-  int* corr_idx;       // [n] target index of the last sweep, -1 = gated out   (original order)
-  float* corr_d2;      // [n] float d2 of the last sweep                        (original order)
-  double* partials;    // [ceil(n / 256)][kNumSums] per-warp sums of one iteration (icp_reduce)
+  float4* cur;         // input_transformed: rewritten in place by every sweep; .w = lower bound on the distance from
+                       // the point to every target point other than its cached neighbours (nncache.cuh)
+  int* corr_idx;       // [n] target index of the last sweep, -1 = gated out
+  float* corr_d2;      // [n] float d2 of the last sweep
+  float4* c0;          // [n] nearest target point found for cur[i]: xyz + original index (int bits, -1 = none)
+  float4* c1;          // [n] runner-up, same layout (nncache.cuh)
+  float4* c2;          // [n] third nearest (used when kCacheK == 3)
+  double* partials;    // [ceil(n / 32)][kNumSums] per-warp sums of one sweep
   IcpState* state;
   int n;
-  int pad;             // 1: cur / c0 / c1 hold the certificate left by the point-to-point loop (read through pos)
-  int ent_off;         // global id of the scan's first query (ids are what the entry sort permutes)
-  int seg;             // segment of the sort key: scans that share a target grid share a segment
-};
-
-// The entry arrays of a batch (all [E], 16-byte aligned, streamed with evict-first accesses).
-struct BatchView {
-  const float4* ent_src;         // source point of the entry (xyz)
-  const unsigned char* ent_sid;  // scan (index into the batch's ScanTask array) of the entry
-  const int* ent_orig;           // original index of the entry inside its scan
-  float4* cur;  // input_transformed: rewritten in place by every sweep; .w = lower bound on the distance from the
-                // point to every target point other than its cached neighbours (nncache.cuh)
-  float4* c0;   // nearest target point found for cur: xyz + original index (int bits, -1 = none)
-  float4* c1;   // runner-up, same layout
-  int E;
-  int nscan;
-  GridView grid;  // the target grid when every scan of the batch shares it (SHARED kernels)
+  int pad;             // 1: c0 / c1 / cur.w hold the certificate of cur (left by the point-to-point loop)
 };
 
 // Per-query state is streamed once per iteration and is larger than what the L2 can keep next to the

@@ -270,144 +270,4 @@ __device__ __forceinline__ void coop_search(const GridView& g, bool want, float 
   }
 }
 
-// ---- slab tiles: the union box of a warp's whole work list, staged ONCE, every lane scanning only its own box ----
-// A cooperative group pays for the union of its lanes' boxes; when the failures of a slab are sparse that union is
-// several times larger than any one lane's box.  A TILE keeps the staging shared (one bulk copy per row of the
-// union box of the whole work list, plus the rows' slices of the cell table) but lets every lane walk just the rows
-// and the x range of its OWN box inside the staged copy — the per-lane search of round 1, with every load now a
-// shared-memory load.
-constexpr int kTileRows = 48;  // (y, z) rows a tile can hold
-constexpr int kTileW = 12;     // cell-table entries per row (cells per row + 1 <= kTileW)
-
-struct Tile {
-  const float4* buf;           // staged points, row after row
-  const int* cs;               // [kTileRows][kTileW] cell_start slices of the rows (absolute sorted positions)
-  const unsigned short* off;   // [kTileRows] first slot of every row
-  int xa, ya, za, ny;          // origin (cells) and rows per z layer
-};
-
-// Stage the tile of the cell box (xa..zb), warp-uniform.  Returns false (nothing staged, the mbarrier untouched) when
-// the box has too many rows, too many cells per row or too many points.
-__device__ __forceinline__ bool tile_stage(const GridView& g, int xa, int xb, int ya, int yb, int za, int zb, float4* buf,
-                                           int* cs, unsigned short* off, unsigned long long* bar, unsigned int& phase) {
-  constexpr unsigned int kFull = 0xFFFFFFFFu;
-  const int lane = threadIdx.x & 31;
-  const int ny = yb - ya + 1, nz = zb - za + 1, nrow = ny * nz, w = xb - xa + 2;
-  if (nrow > kTileRows || w > kTileW || nrow <= 0) return false;
-  // the rows' slices of the cell table, kTileW entries per row (entries past w are never read)
-  for (int k = lane; k < nrow * kTileW; k += 32) {
-    const int r = k / kTileW, x = k - r * kTileW;
-    if (x < w) {
-      const int y = ya + r % ny, z = za + r / ny;
-      cs[k] = __ldg(g.cell_start + (z * g.ny + y) * g.nx + xa + x);
-    }
-  }
-  __syncwarp();
-  // first slot of every row (exclusive prefix of the row lengths; two rows per lane cover kTileRows <= 64)
-  const int r0 = 2 * lane, r1 = 2 * lane + 1;
-  const int s0 = r0 < nrow ? cs[r0 * kTileW] : 0, l0 = r0 < nrow ? cs[r0 * kTileW + w - 1] - s0 : 0;
-  const int s1 = r1 < nrow ? cs[r1 * kTileW] : 0, l1 = r1 < nrow ? cs[r1 * kTileW + w - 1] - s1 : 0;
-  int incl = l0 + l1;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int up = __shfl_up_sync(kFull, incl, o);
-    if (lane >= o) incl += up;
-  }
-  const int total = __shfl_sync(kFull, incl, 31);
-  if (total > kCoopCap) return false;
-  const int o0 = incl - l0 - l1, o1 = o0 + l0;
-  if (r0 < nrow) off[r0] = (unsigned short)o0;
-  if (r1 < nrow) off[r1] = (unsigned short)o1;
-  if (total > 0) {
-    if (lane == 0) mbar_expect_tx(bar, (unsigned int)total * 16u);
-    __syncwarp();
-    if (l0 > 0) bulk_g2s(buf + o0, g.pts + s0, (unsigned int)l0 * 16u, bar);
-    if (l1 > 0) bulk_g2s(buf + o1, g.pts + s1, (unsigned int)l1 * 16u, bar);
-    mbar_wait(bar, phase);
-    phase ^= 1u;
-  }
-  __syncwarp();
-  return true;
-}
-
-// Exact nearest / runner-up / third-distance bound over the cells of `bx` (which lies inside the tile), one lane
-// on its own: the rows of the box are walked by one flattened loop, candidates come from the staged copy.
-// The three-smallest network and its tie rule are those of coop_scan_chunk; a lane that meets a tie rescans its box
-// with the exact bookkeeping.
-__device__ __forceinline__ void tile_search(const GridView& g, const Tile& t, float qx, float qy, float qz, const CellBox& bx,
-                                            CoopTop& out) {
-  coop_init(out);
-  {  // distance from q to the outside of the box (faces that have cells beyond them only)
-    float gmin = INFINITY;
-    if (bx.xa > 0) gmin = fminf(gmin, __fsub_rd(qx, __fadd_ru(g.ox, __fmul_ru((float)bx.xa, g.cell))));
-    if (bx.xb < g.nx - 1) gmin = fminf(gmin, __fsub_rd(__fadd_rd(g.ox, __fmul_rd((float)(bx.xb + 1), g.cell)), qx));
-    if (bx.ya > 0) gmin = fminf(gmin, __fsub_rd(qy, __fadd_ru(g.oy, __fmul_ru((float)bx.ya, g.cell))));
-    if (bx.yb < g.ny - 1) gmin = fminf(gmin, __fsub_rd(__fadd_rd(g.oy, __fmul_rd((float)(bx.yb + 1), g.cell)), qy));
-    if (bx.za > 0) gmin = fminf(gmin, __fsub_rd(qz, __fadd_ru(g.oz, __fmul_ru((float)bx.za, g.cell))));
-    if (bx.zb < g.nz - 1) gmin = fminf(gmin, __fsub_rd(__fadd_rd(g.oz, __fmul_rd((float)(bx.zb + 1), g.cell)), qz));
-    out.lrest = fmaxf(__fsub_rd(gmin, g.slack), 0.0f);
-  }
-  const int nrow = (bx.yb - bx.ya + 1) * (bx.zb - bx.za + 1);
-  const int dxa = bx.xa - t.xa, dxb = bx.xb + 1 - t.xa;
-  int v0 = 0x7FFFFFFF, v1 = 0x7FFFFFFF, v2 = 0x7FFFFFFF;
-  {
-    int y = bx.ya, z = bx.za, k = 0, j = 0, e = 0;
-    for (;;) {
-      if (j >= e) {
-        if (k >= nrow) break;
-        const int r = (z - t.za) * t.ny + (y - t.ya);
-        const int* c = t.cs + r * kTileW;
-        const int base = (int)t.off[r] - c[0];
-        j = base + c[dxa];
-        e = base + c[dxb];
-        ++k;
-        if (++y > bx.yb) {
-          y = bx.ya;
-          ++z;
-        }
-        continue;
-      }
-      const float4 p = t.buf[j];
-      const float d = sqdist3(qx, qy, qz, p.x, p.y, p.z);
-      const int v = (int)((__float_as_uint(d) & 0xFFFFFF00u) | (unsigned int)j);
-      const int t1 = max(v0, v);
-      v0 = min(v0, v);
-      const int t2 = max(v1, t1);
-      v1 = min(v1, t1);
-      v2 = min(v2, t2);
-      ++j;
-    }
-  }
-  const bool tie = v1 != 0x7FFFFFFF && ((v0 ^ v1) >> 8) == 0;
-  if (!tie) {
-    if (v0 != 0x7FFFFFFF) {
-      const int j0 = v0 & 0xFF;
-      const float4 p = t.buf[j0];
-      coop_insert(out, true, sqdist3(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w), j0);
-    }
-    if (v1 != 0x7FFFFFFF) {
-      const int j1 = v1 & 0xFF;
-      const float4 p = t.buf[j1];
-      coop_insert(out, true, sqdist3(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w), j1);
-    }
-    if (v2 != 0x7FFFFFFF) out.b2 = fminf(out.b2, __uint_as_float((unsigned int)v2 & 0xFFFFFF00u));
-  } else {  // exact bookkeeping for every candidate of the box
-    int y = bx.ya, z = bx.za;
-    for (int k = 0; k < nrow; ++k) {
-      const int r = (z - t.za) * t.ny + (y - t.ya);
-      const int* c = t.cs + r * kTileW;
-      const int base = (int)t.off[r] - c[0];
-      for (int j = base + c[dxa]; j < base + c[dxb]; ++j) {
-        const float4 p = t.buf[j];
-        coop_insert(out, true, sqdist3(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w), j);
-      }
-      if (++y > bx.yb) {
-        y = bx.ya;
-        ++z;
-      }
-    }
-  }
-  coop_resolve(out, t.buf);
-}
-
 }  // namespace b2

@@ -593,12 +593,12 @@ int run_gicp(b2icp_handle* h, const float* guess16) {
   ScanTask& t = h->h_tasks[0];
   t.grid = g.view;
   t.src = s.src.raw.as<float4>();
-  t.cur = nullptr;  // pad = 0: getFitnessScore does not read a certificate after GICP
+  t.cur = s.cur.as<float4>();
   t.corr_idx = s.corr_idx.as<int>();
   t.corr_d2 = s.corr_d2.as<float>();
-  t.c0 = nullptr;
-  t.c1 = nullptr;
-  t.pos = nullptr;
+  t.c0 = s.c0.as<float4>();
+  t.c1 = s.c1.as<float4>();
+  t.c2 = s.c2.as<float4>();
   t.partials = s.partials.as<double>();
   t.state = h->states.as<IcpState>();
   t.n = (int)n;

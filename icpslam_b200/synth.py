@@ -308,17 +308,18 @@ def _sample_surfaces(world: World, rng: np.random.Generator, n: int, noise: floa
 
 
 def map_queries(m: dict, config: int, first: int, count: int, trans_sigma: float = 0.08,
-                rot_sigma_deg: float = 0.4):
+                rot_sigma_deg: float = 0.4, variant: int = 0):
     """``count`` sweeps taken after the map of ``build_local_map``, each already moved into the map
     frame by its true pose composed with a small odometry error — what
     OctreeMapper::refineTransformAndGrowMap hands to ICP after `cloud_in_map = raw_pose (x) cloud`
     (reference src/icpslam/octree_mapper.cpp:136).  Returns (list of float32[N,4], list of the 4x4
-    corrections T_fix with  T_fix * query ~ map)."""
+    corrections T_fix with  T_fix * query ~ map).  ``variant`` re-draws the noise of the same poses."""
     out, fixes = [], []
     for j in range(first, first + count):
         idx = m["k"] + j
         pose = m["poses"][idx]
-        rng = np.random.default_rng(1000 * config + 500 + idx)
+        # variant > 0: the same pose seen again with other range noise and another odometry error
+        rng = np.random.default_rng(1000 * config + 500 + idx + 1_000_000 * variant)
         sweep = hdl64_sweep(m["world"], pose, rng)
         err = np.eye(4)
         err[:3, :3] = rot_xyz(*np.radians(rng.normal(0, rot_sigma_deg, 3)))
