@@ -53,8 +53,11 @@ N_SETS = 4             # distinct sets of sweeps the steps rotate through
 PAIRS_PER_RANK = 64    # configs[3] leg: consecutive pairs per rank (8 ranks = the 512 sweeps of BASELINE configs[3])
 
 
+_T0 = time.time()
+
+
 def log(*a):
-    print(*a, file=sys.stderr, flush=True)
+    print(f"[{time.time() - _T0:6.1f}s]", *a, file=sys.stderr, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -249,16 +252,19 @@ def pairs_leg(R, replay, dev, rank, world, local_rank, reps=2):
     records (one collective) and the serial pose composition.  Host sweeps in, records out: end to end."""
     import torch
     import torch.distributed as dist
-    first = rank * PAIRS_PER_RANK
-    cache = f"/tmp/b2icp_bench_cache/pairs_c4_{first}_{PAIRS_PER_RANK + 1}.npy"
+    # The 120 m scene holds ~250 consecutive sweeps of the drive: rank r replays the block of 65 sweeps that starts at
+    # sweep (r mod 3) * 64, with its own range noise (seed offset r), so that 8 ranks hold 8 different recordings.
+    first = (rank % 3) * PAIRS_PER_RANK
+    cache = f"/tmp/b2icp_bench_cache/pairs_c4_{first}_{PAIRS_PER_RANK + 1}_r{rank}.npy"
     if os.path.exists(cache):
         sw = list(np.load(cache))
     else:
-        world_model = synth.make_world(1000 * 4, 4.0)  # a 480 m scene: 8 x 64 consecutive sweeps stay inside it
+        world_model = synth.make_world(1000 * 4)
         poses = synth.trajectory(1000 * 4 + 999, first + PAIRS_PER_RANK + 1)
-        sw = [synth.hdl64_sweep(world_model, poses[i], np.random.default_rng(1000 * 4 + i))
+        sw = [synth.hdl64_sweep(world_model, poses[i], np.random.default_rng(1000 * 4 + i + 1_000_000 * rank))
               for i in range(first, first + PAIRS_PER_RANK + 1)]
         try:
+            os.makedirs(os.path.dirname(cache), exist_ok=True)
             np.save(cache, np.stack(sw))
         except OSError:
             pass
@@ -275,7 +281,7 @@ def pairs_leg(R, replay, dev, rank, world, local_rank, reps=2):
         rc, res = reg.alignBatch(srcs, tgts, with_fitness=True)
         if rc in replay.HARD_ERRORS:
             raise RuntimeError(f"pairs leg: b2icp_align_batch rc={rc}")
-        local = replay.pack_results(res, first)
+        local = replay.pack_results(res, rank * PAIRS_PER_RANK)
         return replay.gather_records(local, n_total, dev), res
 
     once()  # buffers, grids
@@ -396,7 +402,9 @@ def main():
         searches.append(tm.nn_searches)
         iters_hist.append([r.iterations for r in res])
 
+    log("[bench] workload resident; profiled synchronous pass")
     prof_dev_s, gpu_first = timed_sync(args.steps, args.warmup, collect)
+    log("[bench] streamed legs")
 
     # The two timed legs use the streaming form of the batch call (b2icp_align_batch_submit[_device] / _wait): up to
     # --in-flight steps are submitted before the oldest is waited for, each on its own stream.  Every step's copies
@@ -471,7 +479,9 @@ def main():
 
     pairs = None
     if not args.no_pairs:
+        log("[bench] configs[3] leg")
         pairs = pairs_leg(R, replay, dev, rank, world, local_rank)
+    log("[bench] roofline bookkeeping, stand-alone search, CPU sample")
 
     if rank != 0:
         if world > 1:
@@ -579,6 +589,7 @@ def main():
         "cpu_baseline": cpu,
     }
     print(json.dumps(line), flush=True)
+    log("[bench] done")
     if world > 1:
         dist.destroy_process_group()
     if parity is not None and not (parity["iters_equal"] and parity["max_dt"] <= 1e-4 and parity["max_dr"] <= 1e-4):

@@ -78,8 +78,10 @@ struct DeviceBuf {
 
 struct Cloud {
   DeviceBuf raw;  // float4[n] as uploaded
+  const float4* ext = nullptr;  // a caller's device cloud used in place (streamed device batches); raw is unused then
   size_t n = 0;
   bool valid = false;
+  const float4* dev() const { return ext ? ext : raw.as<float4>(); }
 };
 
 struct GridSlot {
@@ -131,6 +133,18 @@ __global__ void export_records(const IcpState* __restrict__ st, int B, int with_
 
 }  // namespace
 
+// A captured ICP loop (task / state upload, one sweep per iteration, write-out) and the shape it was captured for.
+struct GraphKey {
+  int B, iters, qpt, streamed, sched;
+  size_t max_n;
+  IcpConfig cfg;
+};
+struct GraphCache {
+  cudaGraphExec_t exec = nullptr;
+  GraphKey exec_key, last_key;
+  bool has_last = false;
+};
+
 struct b2icp_handle {
   b2icp_params params;
   IcpConfig cfg;
@@ -171,6 +185,10 @@ struct b2icp_handle {
   int max_in_flight = kStreamSets;  // B2ICP_IN_FLIGHT environment variable (tuning only)
   int qpt_override = 0;  // B2ICP_QPT environment variable (tuning only)
   std::vector<int> qpt_sched;  // B2ICP_QPT_SCHED="2,4,8": slab length per iteration, last value repeats (tuning only)
+  GraphCache graphs[kStreamSets + 1];  // one per streamed slot set, the last one for synchronous calls
+  cudaStream_t capture_stream = nullptr;
+  bool use_graphs = true;  // B2ICP_NO_GRAPH switches the captured loops off (tuning / debugging only)
+  long long graph_launches = 0;
   b2icp_record* sink = nullptr;  // b2icp_set_record_sink: device records of streamed batches
   size_t sink_cap = 0, sink_used = 0;
   int w_override = 0;  // B2ICP_W: lanes per cooperative group of the stand-alone search, 8 or 32 (tuning only)
@@ -365,6 +383,7 @@ int upload_cloud(b2icp_handle* h, Cloud& c, const float* xyzw, size_t n, bool fr
   CK(c.raw.ensure(n * sizeof(float4)));
   CK(cudaMemcpyAsync(c.raw.p, xyzw, n * sizeof(float4), from_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
                      on ? on : h->stream));
+  c.ext = nullptr;
   c.n = n;
   c.valid = true;
   return B2ICP_OK;
@@ -431,7 +450,7 @@ int run_batch(b2icp_handle* h, int B, const float* guesses, int slot0 = 0, bool 
     max_dim = std::max(max_dim, std::max(g.view.nx, std::max(g.view.ny, g.view.nz)));
     ScanTask& t = h->h_tasks[slot0 + i];
     t.grid = g.view;
-    t.src = s.src.raw.as<float4>();
+    t.src = s.src.dev();
     t.cur = s.cur.as<float4>();
     t.corr_idx = s.corr_idx.as<int>();
     t.corr_d2 = s.corr_d2.as<float>();
@@ -455,9 +474,6 @@ int run_batch(b2icp_handle* h, int B, const float* guesses, int slot0 = 0, bool 
   // An unbounded gate (PCL's own default, sqrt(DBL_MAX)) has no radius to clamp a search to: the box of a query
   // with nothing nearby may then grow to the whole grid — exact, slow, and off the reference's 1.0 m path.
   h->cfg.max_rings = std::isfinite(h->cfg.bound2) ? rings_for_bound(h, min_cell) + (int)std::ceil(h->cfg.margin_frac) + 1 : max_dim;
-  CK(cudaMemcpyAsync(h->tasks.as<ScanTask>() + slot0, h->h_tasks + slot0, sizeof(ScanTask) * B, cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemcpyAsync(h->states.as<IcpState>() + slot0, h->h_states + slot0, sizeof(IcpState) * B, cudaMemcpyHostToDevice, h->stream));
-
   const bool prof = allow_prof && h->params.profile != 0;
   const int iters = std::max(h->params.max_iterations, 1);
   if (prof) {
@@ -466,7 +482,6 @@ int run_batch(b2icp_handle* h, int B, const float* guesses, int slot0 = 0, bool 
       CK(cudaEventCreate(&e));
       h->events.push_back(e);
     }
-    CK(cudaEventRecord(h->events[0], h->stream));
   }
   // queries per lane (a warp owns 32 * qpt consecutive queries): long slabs amortise the reduction and keep
   // the lanes of the search phase busy; short ones are for launches that could not fill the SMs otherwise
@@ -487,30 +502,82 @@ int run_batch(b2icp_handle* h, int B, const float* guesses, int slot0 = 0, bool 
     if (streamed) return qpt;
     return it == 0 ? std::min(qpt, kFirstSweepQpt) : (it <= 4 ? std::min(qpt, 4) : qpt);
   };
-  for (int it = 0; it < iters; ++it) {
-    if (prof) CK(cudaEventRecord(h->events[2 + 2 * it], h->stream));
-    const int q = qpt_at(it);
-    const dim3 grid((unsigned)((max_n + (size_t)kSweepThreads * q - 1) / ((size_t)kSweepThreads * q)), (unsigned)B, 1);
-    if (q == 32)
-      icp_sweep_p2p<32><<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
-    else if (q == 16)
-      icp_sweep_p2p<16><<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
-    else if (q == 8)
-      icp_sweep_p2p<8><<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
-    else if (q == 4)
-      icp_sweep_p2p<4><<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
-    else if (q == 2)
-      icp_sweep_p2p<2><<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
-    else
-      icp_sweep_p2p<1><<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
-    if (prof) CK(cudaEventRecord(h->events[3 + 2 * it], h->stream));
-  }
-  {  // correspondences of the last sweep, for b2icp_get_correspondences
+  // task / state upload + one sweep per iteration + the correspondence write-out, in order on `st`
+  auto enqueue_loop = [&](cudaStream_t st, bool with_events) -> cudaError_t {
+    cudaError_t e = cudaMemcpyAsync(h->tasks.as<ScanTask>() + slot0, h->h_tasks + slot0, sizeof(ScanTask) * B, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyAsync(h->states.as<IcpState>() + slot0, h->h_states + slot0, sizeof(IcpState) * B, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    for (int it = 0; it < iters; ++it) {
+      if (with_events) cudaEventRecord(h->events[2 + 2 * it], st);
+      const int q = qpt_at(it);
+      const dim3 grid((unsigned)((max_n + (size_t)kSweepThreads * q - 1) / ((size_t)kSweepThreads * q)), (unsigned)B, 1);
+      if (q == 32)
+        icp_sweep_p2p<32><<<grid, kSweepThreads, 0, st>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
+      else if (q == 16)
+        icp_sweep_p2p<16><<<grid, kSweepThreads, 0, st>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
+      else if (q == 8)
+        icp_sweep_p2p<8><<<grid, kSweepThreads, 0, st>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
+      else if (q == 4)
+        icp_sweep_p2p<4><<<grid, kSweepThreads, 0, st>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
+      else if (q == 2)
+        icp_sweep_p2p<2><<<grid, kSweepThreads, 0, st>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
+      else
+        icp_sweep_p2p<1><<<grid, kSweepThreads, 0, st>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
+      if (with_events) cudaEventRecord(h->events[3 + 2 * it], st);
+    }
+    // correspondences of the last sweep, for b2icp_get_correspondences
     const dim3 fgrid((unsigned)((max_n + 255) / 256), (unsigned)B, 1);
-    icp_finalize_corr<<<fgrid, 256, 0, h->stream>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
+    icp_finalize_corr<<<fgrid, 256, 0, st>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
+    return cudaSuccess;
+  };
+  // The loop is the same 32 operations every time a batch of this shape comes back (streamed replay, the
+  // odometer's scan after scan): the second time a shape is seen its loop is captured into a CUDA graph, and from
+  // then on one graph launch replaces the 32 stream operations — the host cost per batch no longer grows with the
+  // iteration count, which is what kept 8 ranks on one 16-core host from scaling (profiles/r02_scaling.md).
+  bool launched = false;
+  if (!prof && h->use_graphs) {
+    GraphKey key;
+    std::memset(&key, 0, sizeof(key));
+    key.B = B;
+    key.iters = iters;
+    key.qpt = qpt;
+    key.streamed = streamed ? 1 : 0;
+    key.max_n = max_n;
+    key.cfg = h->cfg;
+    key.sched = h->qpt_sched.empty() ? 0 : 1;
+    GraphCache& gc = h->graphs[streamed ? slot0 / kSetSlots : kStreamSets];
+    if (!(gc.exec && std::memcmp(&gc.exec_key, &key, sizeof(key)) == 0) && gc.has_last &&
+        std::memcmp(&gc.last_key, &key, sizeof(key)) == 0) {
+      if (!h->capture_stream) CK(cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking));
+      if (gc.exec) cudaGraphExecDestroy(gc.exec);
+      gc.exec = nullptr;
+      cudaGraph_t graph = nullptr;
+      CK(cudaStreamBeginCapture(h->capture_stream, cudaStreamCaptureModeRelaxed));
+      const cudaError_t ce = enqueue_loop(h->capture_stream, false);
+      const cudaError_t ee = cudaStreamEndCapture(h->capture_stream, &graph);
+      if (ce == cudaSuccess && ee == cudaSuccess && graph && cudaGraphInstantiate(&gc.exec, graph, 0) == cudaSuccess) {
+        gc.exec_key = key;
+      } else {
+        gc.exec = nullptr;
+        cudaGetLastError();
+      }
+      if (graph) cudaGraphDestroy(graph);
+    }
+    gc.last_key = key;
+    gc.has_last = true;
+    if (gc.exec && std::memcmp(&gc.exec_key, &key, sizeof(key)) == 0) {
+      CK(cudaGraphLaunch(gc.exec, h->stream));
+      h->graph_launches += 1;
+      launched = true;
+    }
+  }
+  if (!launched) {
+    if (prof) CK(cudaEventRecord(h->events[0], h->stream));
+    CK(enqueue_loop(h->stream, prof));
+    if (prof) CK(cudaEventRecord(h->events[1], h->stream));
   }
   h->launches += iters + 1;
-  if (prof) CK(cudaEventRecord(h->events[1], h->stream));
   h->last_batch = B;
   return B2ICP_OK;
 }
@@ -851,6 +918,7 @@ int b2icp_create(const b2icp_params* p, b2icp_handle** out) {
   std::memset(&h->timing, 0, sizeof(h->timing));
   derive_config(h);
   if (const char* e = getenv("B2ICP_QPT")) h->qpt_override = atoi(e);
+  if (getenv("B2ICP_NO_GRAPH")) h->use_graphs = false;
   if (const char* e = getenv("B2ICP_W")) h->w_override = atoi(e);
   if (const char* e = getenv("B2ICP_JOIN")) h->join_d = atoi(e);
   if (const char* e = getenv("B2ICP_IN_FLIGHT")) h->max_in_flight = std::max(1, std::min(kStreamSets, atoi(e)));
@@ -911,6 +979,9 @@ int b2icp_destroy(b2icp_handle* h) {
     cudaStreamSynchronize(h->copy_stream);
     cudaStreamDestroy(h->copy_stream);
   }
+  for (GraphCache& gc : h->graphs)
+    if (gc.exec) cudaGraphExecDestroy(gc.exec);
+  if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
   if (h->h_states) cudaFreeHost(h->h_states);
   if (h->h_tasks) cudaFreeHost(h->h_tasks);
   if (h->h_bbox) cudaFreeHost(h->h_bbox);
@@ -977,7 +1048,7 @@ int b2icp_promote_source_to_target(b2icp_handle* h) {
   CK(cudaSetDevice(h->device));
   ScanSlot& s = slot(h, 0);
   GridSlot& g = gslot(h, 0);
-  if (!s.src.valid) return fail(h, B2ICP_ERR_NO_SOURCE, "no source cloud set");
+  if (!s.src.valid || s.src.ext) return fail(h, B2ICP_ERR_NO_SOURCE, "no source cloud set");
   std::swap(s.src.raw, g.tgt.raw);
   g.tgt.n = s.src.n;
   g.tgt.valid = true;
@@ -1010,7 +1081,7 @@ int b2icp_align(b2icp_handle* h, const float* guess, b2icp_result* out, float* a
   if (aligned_xyzw) {
     CK(h->xf_out.ensure(n * sizeof(float4)));
     transform_cloud_f<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(
-        s.src.raw.as<float4>(), (int)n, h->states.as<IcpState>()->final_T, h->xf_out.as<float4>());
+        s.src.dev(), (int)n, h->states.as<IcpState>()->final_T, h->xf_out.as<float4>());
     h->launches += 1;
     CK(cudaMemcpyAsync(aligned_xyzw, h->xf_out.p, n * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
   }
@@ -1189,6 +1260,14 @@ static int submit_impl(b2icp_handle* h, const float* const* src, const size_t* n
   for (int i = 0; i < B; ++i) {
     ScanSlot& s = slot(h, (size_t)(slot0 + i));
     s.grid = 0;
+    if (from_device) {  // the caller's device cloud is read in place: it must stay valid until the batch's _wait
+      if (!src[i] || n_src[i] == 0) return fail(h, B2ICP_ERR_EMPTY_CLOUD, "empty cloud");
+      if (n_src[i] > (size_t)INT32_MAX / 8) return fail(h, B2ICP_ERR_INVALID_ARG, "cloud too large");
+      s.src.ext = reinterpret_cast<const float4*>(src[i]);
+      s.src.n = n_src[i];
+      s.src.valid = true;
+      continue;
+    }
     int rc = upload_cloud(h, s.src, src[i], n_src[i], from_device, up);
     if (rc) {
       cudaStreamSynchronize(up);

@@ -201,7 +201,8 @@ int b2icp_voxel_filter(b2icp_handle* h, const float* in_xyzw, size_t n, float le
  * in submission order).  Up to B2ICP_MAX_IN_FLIGHT batches may be in flight (each on its own stream), so the PCIe
  * transfer of the next batches overlaps the sweeps of the current one and the sparse late iterations of one batch
  * share the device with the first iterations of the next.  The host clouds of a batch must stay valid (and should be page-locked, b2icp_host_alloc) until its
- * _wait returns.  The synchronous calls must not be mixed in while batches are in flight. */
+ * _wait returns; the DEVICE clouds of _submit_device are read in place (no copy) and must stay valid and unchanged
+ * until then too.  The synchronous calls must not be mixed in while batches are in flight. */
 #define B2ICP_MAX_IN_FLIGHT 8
 int b2icp_align_batch_submit(b2icp_handle* h, const float* const* src, const size_t* n_src, size_t batch, int with_fitness);
 int b2icp_align_batch_submit_device(b2icp_handle* h, const float* const* d_src, const size_t* n_src, size_t batch,
