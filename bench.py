@@ -343,10 +343,12 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     Bn = args.batch
-    # every rank casts its own sweeps (in parallel): rank r owns the B poses r*B .. r*B+B-1 after the map (as in round 1);
-    # its N_SETS sets are those poses seen N_SETS times with independent range noise and odometry errors — distinct
-    # inputs of the same difficulty, so that the steps sample the variance across inputs
-    keys = [(rank * Bn, v) for v in range(N_SETS)]
+    # Every rank casts its own sweeps (in parallel).  All ranks see the SAME B poses (the first B after the map) and
+    # differ in the range noise and odometry error drawn for them: rank r owns noise variants r*N_SETS .. r*N_SETS+3.
+    # Weak scaling needs equal work per rank: in round 1 rank r took poses r*B .. r*B+B-1, which lie farther and
+    # farther from the mapped area and need more iterations (profiles/r02_scaling.md) — the slowest rank then set
+    # the step time and the curve read as a scaling loss.
+    keys = [(0, rank * N_SETS + v) for v in range(N_SETS)]
     loaded = prepare_workloads(keys, Bn)
     map_xyzw = loaded[keys[0]][0]
     sets = [loaded[k][1] for k in keys]
@@ -410,18 +412,25 @@ def main():
     # --in-flight steps are submitted before the oldest is waited for, each on its own stream.  Every step's copies
     # (H2D of its sweeps, D2H of its results), the L2 flush between steps and — with more than one rank — the ONE
     # gather of all records at the end are inside the timed region: one event pair around all K steps.
+    host = {"submit_s": 0.0, "wait_s": 0.0}
+    no_flush = os.environ.get("BENCH_NO_FLUSH") is not None  # diagnostics only
+
     def run_streamed(steps, submit):
         submitted = done = 0
         while done < steps:
+            t0 = time.perf_counter()
             while submitted < steps and submitted - done < args.in_flight:
-                if submitted:
+                if submitted and not no_flush:
                     flush.zero_()
                 if submit(submitted):
                     raise RuntimeError("b2icp_align_batch_submit failed")
                 submitted += 1
+            t1 = time.perf_counter()
             rc, res = reg.alignBatchWait()
             if rc:
                 raise RuntimeError(f"b2icp_align_batch_wait rc={rc}")
+            host["submit_s"] += t1 - t0
+            host["wait_s"] += time.perf_counter() - t1
             done += 1
 
     rec_words = R.RECORD_DTYPE.itemsize // 4
@@ -439,8 +448,10 @@ def main():
         reg.setRecordSink(sink.data_ptr(), cap)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n0 = reg.timing().kernel_launches
+        host["submit_s"] = host["wait_s"] = 0.0
         e0.record(stream)
         run_streamed(steps, submit)
+        timed_streamed.host = dict(host)
         if world > 1:  # every batch has been waited for: its records are in `sink`
             with torch.cuda.stream(side):
                 dist.all_gather_into_tensor(gathered, sink)
@@ -465,6 +476,9 @@ def main():
         sampler.start()
     dev_s = timed_streamed(lambda k: reg.alignBatchSubmitDevice(d_ptrs[k % N_SETS], n_src), args.steps, args.warmup)
     launches = timed_streamed.launches  # the launches of the K timed steps only
+    host_resident = timed_streamed.host
+    log(f"[bench] rank {rank}: resident leg {1e3 * dev_s / args.steps:.3f} ms/step; host per step: submit "
+        f"{1e3 * host_resident['submit_s'] / args.steps:.3f} ms, wait {1e3 * host_resident['wait_s'] / args.steps:.3f} ms")
     clocks = sampler.stop() if rank == 0 else None
     value = world * Bn * args.steps / dev_s
     # the records of the resident leg as the ranks exchanged them (rank 0 checks them against what _wait returned)
@@ -549,7 +563,8 @@ def main():
         "grid_cell_m": grid["cell"], "grid_dims": list(grid["dims"]), "grid_occupancy": grid["occupancy"],
         "mean_iterations": float(its_all.mean()), "max_iterations_seen": int(its_all.max()), "api": api,
         "synchronous_call_scans_per_s": world * Bn * args.steps / prof_dev_s,
-        "gathered_records_ok": rec_ok}
+        "gathered_records_ok": rec_ok,
+        "host_ms_per_step": {"submit": 1e3 * host_resident["submit_s"] / args.steps, "wait": 1e3 * host_resident["wait_s"] / args.steps}}
 
     # ---- CPU baseline on this box's host cores (bounded sample) + parity of the same sweeps ---------
     cpu, parity = None, None

@@ -12,6 +12,7 @@
 #include "../../include/b2icp.h"
 
 #include <cuda_runtime.h>
+#include <ucontext.h>
 
 #include <algorithm>
 #include <cfloat>
@@ -193,9 +194,12 @@ struct b2icp_handle {
   size_t sink_cap = 0, sink_used = 0;
   int w_override = 0;  // B2ICP_W: lanes per cooperative group of the stand-alone search, 8 or 32 (tuning only)
   int join_d = 4;      // B2ICP_JOIN: cells of slack inside which a lane joins its group's pass (tuning only)
-  double* h_gicp_partials = nullptr;  // pinned read-back of gicp_fdf_kernel's per-CTA sums
+  double* h_gicp_partials = nullptr;  // pinned read-back of the GICP rounds: 14 sums per scan
   size_t h_gicp_partials_cap = 0;
-  long gicp_evals = 0;
+  void* h_gicp_tasks = nullptr;  // pinned task arrays of a GICP round (gicp_host.inl)
+  size_t h_gicp_tasks_cap = 0;
+  DeviceBuf gicp_tasks;
+  long gicp_evals = 0, gicp_rounds = 0;
 };
 
 namespace {
@@ -725,58 +729,89 @@ int streamed_sync_batch(b2icp_handle* h, const float* const* src, const size_t* 
   return worst;
 }
 
-// GICP over a batch: the scans run one after the other through slot 0 (the BFGS recursion is driven from the
-// host, gicp_host.inl), with the same target conventions as the point-to-point batch.
+// GICP over a batch: chunks of up to 32 scans whose BFGS recursions advance in lockstep rounds (gicp_host.inl), with
+// the same target conventions as the point-to-point batch.
 int gicp_batch_impl(b2icp_handle* h, const float* const* src, const size_t* n_src, const float* const* tgt,
                     const size_t* n_tgt, size_t batch, int with_fitness, b2icp_result* out, bool from_device) {
   const bool shared_target = (tgt == nullptr);
   if ((shared_target || !tgt[0]) && !gslot(h, 0).valid) return fail(h, B2ICP_ERR_NO_TARGET, "no target cloud set");
   int worst = B2ICP_OK;
   h->aligned = false;
-  ScanSlot& s = slot(h, 0);
-  for (size_t i = 0; i < batch; ++i) {
-    s.grid = 0;
-    if (!shared_target && (tgt[i] || i > 0)) {
+  constexpr int kChunk = kSetSlots;
+  for (size_t base = 0; base < batch; base += kChunk) {
+    const int B = (int)std::min<size_t>(kChunk, batch - base);
+    const bool carry = !shared_target && base > 0 && !tgt[base];
+    if (carry) {  // consecutive sweeps across a chunk border: the last source of the previous chunk is the target
       GridSlot& g1 = gslot(h, 1);
-      size_t tn = 0;
-      if (tgt[i]) {
-        tn = n_tgt ? n_tgt[i] : 0;
-        int rc = upload_cloud(h, g1.tgt, tgt[i], tn, from_device);
-        if (rc) return rc;
-      } else {  // consecutive sweeps: the previous source becomes the target
-        std::swap(g1.tgt.raw, s.src.raw);
-        tn = g1.tgt.n = s.src.n;
-        g1.tgt.valid = true;
-        s.src.valid = false;
+      ScanSlot& last = slot(h, kChunk - 1);
+      std::swap(g1.tgt.raw, last.src.raw);
+      g1.tgt.n = last.src.n;
+      g1.tgt.valid = true;
+      last.src.valid = false;
+    }
+    for (int i = 0; i < B; ++i) {
+      int rc = upload_cloud(h, slot(h, i).src, src[base + i], n_src[base + i], from_device);
+      if (rc) return rc;
+    }
+    if (shared_target) {
+      for (int i = 0; i < B; ++i) slot(h, i).grid = 0;
+    } else {
+      std::vector<GridSlot*> gl;
+      std::vector<size_t> nl;
+      for (int i = 0; i < B; ++i) {
+        const size_t gi = 1 + (size_t)i;  // grid 0 stays the handle's own target
+        GridSlot& g = gslot(h, gi);
+        const float* tp = tgt[base + i];
+        size_t tn = 0;
+        if (tp) {
+          tn = n_tgt ? n_tgt[base + i] : 0;
+          int rc = upload_cloud(h, g.tgt, tp, tn, from_device);
+          if (rc) return rc;
+          g.pts = g.tgt.raw.as<float4>();
+        } else if (i > 0) {
+          g.pts = slot(h, i - 1).src.raw.as<float4>();
+          tn = slot(h, i - 1).src.n;
+        } else if (carry) {
+          g.pts = g.tgt.raw.as<float4>();
+          tn = g.tgt.n;
+        } else {
+          slot(h, i).grid = 0;  // pair 0 without a target: the handle's current target
+          continue;
+        }
+        slot(h, i).grid = (int)gi;
+        gl.push_back(&g);
+        nl.push_back(tn);
       }
-      g1.pts = g1.tgt.raw.as<float4>();
-      GridSlot* gp = &g1;
-      int rc = build_grids(h, &gp, &tn, 1);
-      if (rc) return rc;
-      s.grid = 1;
+      if (!gl.empty()) {
+        int rc = build_grids(h, gl.data(), nl.data(), (int)gl.size());
+        if (rc) return rc;
+      }
     }
-    int rc = upload_cloud(h, s.src, src[i], n_src[i], from_device);
-    if (rc) return rc;
-    rc = run_gicp(h, nullptr);
-    if (rc) {  // hard failure of this pair (too few points, CUDA): reported, the batch goes on
-      out[i].status_detail = rc;
-      if (worst == B2ICP_OK) worst = rc;
-      if (rc == B2ICP_ERR_CUDA) return rc;
-      continue;
+    int rc = run_gicp_batch(h, B, nullptr);
+    if (rc == B2ICP_ERR_CUDA) return rc;
+    if (rc && worst == B2ICP_OK) worst = rc;
+    for (int i = 0; i < B; ++i) {
+      fill_result(h->h_states[i], &out[base + i]);
+      const int status = h->h_states[i].status;
+      if (status != 0 && worst == B2ICP_OK) {
+        worst = status;
+        h->err = status_message(worst);
+      }
     }
-    CK(cudaStreamSynchronize(h->stream));
-    fill_result(h->h_states[0], &out[i]);
-    const int status = h->h_states[0].status;
-    if (with_fitness && status == 0) {
-      rc = enqueue_fitness(h, 0, DBL_MAX);
-      if (rc) return rc;
-      CK(cudaMemcpyAsync(h->h_states, h->states.p, sizeof(IcpState), cudaMemcpyDeviceToHost, h->stream));
-      CK(cudaStreamSynchronize(h->stream));
-      out[i].fitness = fitness_value(h->h_states[0]);
-    }
-    if (status != 0 && worst == B2ICP_OK) {
-      worst = status;
-      h->err = status_message(worst);
+    if (with_fitness) {
+      bool any = false;
+      for (int i = 0; i < B; ++i)
+        if (h->h_states[i].status == 0) {
+          rc = enqueue_fitness(h, i, DBL_MAX);
+          if (rc) return rc;
+          any = true;
+        }
+      if (any) {
+        CK(cudaMemcpyAsync(h->h_states, h->states.p, sizeof(IcpState) * B, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        for (int i = 0; i < B; ++i)
+          if (h->h_states[i].status == 0) out[base + i].fitness = fitness_value(h->h_states[i]);
+      }
     }
   }
   CK(cudaGetLastError());
@@ -986,6 +1021,8 @@ int b2icp_destroy(b2icp_handle* h) {
   if (h->h_tasks) cudaFreeHost(h->h_tasks);
   if (h->h_bbox) cudaFreeHost(h->h_bbox);
   if (h->h_gicp_partials) cudaFreeHost(h->h_gicp_partials);
+  if (h->h_gicp_tasks) cudaFreeHost(h->h_gicp_tasks);
+  h->gicp_tasks.release();
   if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
   return B2ICP_OK;

@@ -6,15 +6,17 @@
 //   G2  gicp_corr_kernel    per outer iteration: query = transformation_ * (guess * p) in float, exact
 //                           1-NN (nn.cuh), strict gate d2 < max^2, M = (R C1 R^T + C2)^-1
 //   G3  gicp_fdf_kernel     one evaluation of the BFGS cost functor (f, df in one pass): 13 sums
-// The BFGS recursion itself is O(1) scalar work and runs on the host (gicp_host.hpp).
+// The BFGS recursion itself is O(1) scalar work and runs on the host (gicp_host.inl), one fiber per scan.
 //
 // PCL's GICP does not survive a change in the last bit of f (its line search ends on a round-off
 // test), so everything here is written to be BIT-IDENTICAL to a fixed arithmetic definition:
 //   * every double operation is an explicit __dmul_rn / __dadd_rn / __dsub_rn / __ddiv_rn / __dsqrt_rn in
 //     the order of the C expression it restates (no FMA contraction, no reassociation);
 //   * neighbour sums run in (d2, index) order; cross-point sums use a fixed tree: 256-point CTAs, xor
-//     butterfly 16,8,4,2,1 inside each warp, the 8 warp sums added in order, CTA sums added in order on
-//     the host.
+//     butterfly 16,8,4,2,1 inside each warp, the 8 warp sums added in order, CTA sums added in order
+//     (gicp_sum_kernel).
+// Every kernel takes an array of per-scan tasks (blockIdx.y = scan): the scans of a batch advance together, one
+// launch per evaluation ROUND instead of one per scan (gicp_host.inl).
 #pragma once
 #include "common.cuh"
 #include "nn.cuh"
@@ -311,34 +313,47 @@ struct GicpIterArgs {
   int use_seed;
 };
 
-__global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas)
-    gicp_corr_kernel(GridView g, const float4* __restrict__ src, int n, GicpIterArgs a,
-                     const double* __restrict__ cov_src, const double* __restrict__ cov_tgt,
-                     double* __restrict__ mahal, int* __restrict__ corr_idx, float* __restrict__ corr_d2,
-                     int* __restrict__ corr_pos) {
+// One task = one scan of a GICP batch (blockIdx.y selects it): every scan of the batch advances with the same launch.
+struct GicpCorrTask {
+  GridView g;
+  const float4* src;
+  const double* cov_src;
+  const double* cov_tgt;
+  double* mahal;
+  int* corr_idx;
+  float* corr_d2;
+  int* corr_pos;
+  int n;
+  int pad;
+  GicpIterArgs a;
+};
+
+__global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) gicp_corr_kernel(const GicpCorrTask* __restrict__ tasks) {
   __shared__ NNScratch<kSweepThreads> sc;
+  const GicpCorrTask& t = tasks[blockIdx.y];
+  const GicpIterArgs& a = t.a;
   const int i = blockIdx.x * kSweepThreads + threadIdx.x;
-  if (i >= n) return;
-  const float4 p = __ldg(src + i);
+  if (i >= t.n) return;
+  const float4 p = __ldg(t.src + i);
   const float4 q0 = xform_f(a.guess, p.x, p.y, p.z);
   const float4 q = xform_f(a.T, q0.x, q0.y, q0.z);
   NNResult r;
   r.key = kInfKey;
   r.pos = -1;
   if (isfinite(q.x) && isfinite(q.y) && isfinite(q.z))
-    r = grid_nn<kSweepThreads>(g, q.x, q.y, q.z, a.bound2, a.max_rings, a.use_seed ? corr_pos[i] : -1, sc);
+    r = grid_nn<kSweepThreads>(t.g, q.x, q.y, q.z, a.bound2, a.max_rings, a.use_seed ? t.corr_pos[i] : -1, sc);
   const float d2 = key_d2(r.key);
   const bool keep = (r.key != kInfKey) && ((double)d2 < a.max2);
   const int ti = key_idx(r.key);
-  corr_idx[i] = keep ? ti : -1;
-  corr_d2[i] = d2;
-  corr_pos[i] = r.pos;
+  t.corr_idx[i] = keep ? ti : -1;
+  t.corr_d2[i] = d2;
+  t.corr_pos[i] = r.pos;
   if (!keep) return;
   double C1[9], C2[9], M[9], temp[9];
 #pragma unroll
   for (int e = 0; e < 9; ++e) {
-    C1[e] = cov_src[(size_t)9 * i + e];
-    C2[e] = cov_tgt[(size_t)9 * ti + e];
+    C1[e] = t.cov_src[(size_t)9 * i + e];
+    C2[e] = t.cov_tgt[(size_t)9 * ti + e];
   }
   mat3_mul(a.R, C1, M);
   mat3_mul_bt(M, a.R, temp);
@@ -346,7 +361,7 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas)
   for (int e = 0; e < 9; ++e) temp[e] = dadd(temp[e], C2[e]);
   mat3_inv(temp, M);
 #pragma unroll
-  for (int e = 0; e < 9; ++e) mahal[(size_t)9 * i + e] = M[e];
+  for (int e = 0; e < 9; ++e) t.mahal[(size_t)9 * i + e] = M[e];
 }
 
 // ---- G3: one evaluation of the cost functor (OptimizationFunctorWithIndices::fdf) ---------------------
@@ -355,23 +370,35 @@ struct GicpEvalArgs {
   float base[16];  // base_transformation_
 };
 
-__global__ void __launch_bounds__(kGicpThreads) gicp_fdf_kernel(const float4* __restrict__ src,
-                                                                const float4* __restrict__ tgt, int n, GicpEvalArgs a,
-                                                                const int* __restrict__ corr_idx,
-                                                                const double* __restrict__ mahal,
-                                                                double* __restrict__ partials) {
+struct GicpFdfTask {
+  const float4* src;
+  const float4* tgt;
+  const int* corr_idx;
+  const double* mahal;
+  double* partials;  // [ceil(n / 256)][kGicpSums]
+  double* sums;      // [kGicpSums]: the CTA sums added in order (gicp_sum_kernel)
+  int n;
+  int pad;
+  GicpEvalArgs a;
+};
+
+__global__ void __launch_bounds__(kGicpThreads) gicp_fdf_kernel(const GicpFdfTask* __restrict__ tasks) {
   __shared__ double smem[kGicpThreads / 32][kGicpSums];
+  const GicpFdfTask& t = tasks[blockIdx.y];
+  const GicpEvalArgs& a = t.a;
+  const int n = t.n;
+  if (blockIdx.x * kGicpThreads >= n) return;
   const int i = blockIdx.x * kGicpThreads + threadIdx.x;
   double v[kGicpSums];
 #pragma unroll
   for (int c = 0; c < kGicpSums; ++c) v[c] = 0.0;
-  const int ti = i < n ? corr_idx[i] : -1;
+  const int ti = i < n ? t.corr_idx[i] : -1;
   if (ti >= 0) {
-    const float4 ps = __ldg(src + i);
-    const float4 pt = __ldg(tgt + ti);
+    const float4 ps = __ldg(t.src + i);
+    const float4 pt = __ldg(t.tgt + ti);
     const float4 pp = xform_f(a.Tx, ps.x, ps.y, ps.z);
     const double r0 = (double)fsub(pp.x, pt.x), r1 = (double)fsub(pp.y, pt.y), r2 = (double)fsub(pp.z, pt.z);
-    const double* M = mahal + (size_t)9 * i;
+    const double* M = t.mahal + (size_t)9 * i;
     const double t0 = dadd(dadd(dmul(M[0], r0), dmul(M[1], r1)), dmul(M[2], r2));
     const double t1 = dadd(dadd(dmul(M[3], r0), dmul(M[4], r1)), dmul(M[5], r2));
     const double t2 = dadd(dadd(dmul(M[6], r0), dmul(M[7], r1)), dmul(M[8], r2));
@@ -386,7 +413,7 @@ __global__ void __launch_bounds__(kGicpThreads) gicp_fdf_kernel(const float4* __
     v[10] = dmul(b2, t0); v[11] = dmul(b2, t1); v[12] = dmul(b2, t2);
     v[13] = 1.0;
   }
-  // the fixed tree: xor butterfly inside the warp, warp sums in order, CTA sums in order (host)
+  // the fixed tree: xor butterfly inside the warp, warp sums in order, CTA sums in order (gicp_sum_kernel)
 #pragma unroll
   for (int c = 0; c < kGicpSums; ++c) {
 #pragma unroll
@@ -402,8 +429,19 @@ __global__ void __launch_bounds__(kGicpThreads) gicp_fdf_kernel(const float4* __
     double s = 0.0;
 #pragma unroll
     for (int w = 0; w < kGicpThreads / 32; ++w) s = dadd(s, smem[w][threadIdx.x]);
-    partials[(size_t)blockIdx.x * kGicpSums + threadIdx.x] = s;
+    t.partials[(size_t)blockIdx.x * kGicpSums + threadIdx.x] = s;
   }
+}
+
+// The last level of the tree: the CTA sums of a scan added in CTA order (what the host loop of round 1 did after a
+// read-back of every partial; now 14 doubles per scan come back instead of 14 per CTA).
+__global__ void __launch_bounds__(32) gicp_sum_kernel(const GicpFdfTask* __restrict__ tasks) {
+  const GicpFdfTask& t = tasks[blockIdx.x];
+  if (threadIdx.x >= kGicpSums) return;
+  const int nblk = (t.n + kGicpThreads - 1) / kGicpThreads;
+  double tot = 0.0;
+  for (int b = 0; b < nblk; ++b) tot = dadd(tot, t.partials[(size_t)b * kGicpSums + threadIdx.x]);
+  t.sums[threadIdx.x] = tot;
 }
 
 }  // namespace b2

@@ -3,14 +3,25 @@
 // pcl::GeneralizedIterativeClosestPoint::computeTransformation's outer loop and PCL's BFGS (a port of GSL
 // vector_bfgs2 + linear_minimize.c) are O(1) scalar work per step and run here
 // on the host in double precision with the C library's sin / cos / atan2 — the only per-point work, the
-// cost functor, is one launch of gicp_fdf_kernel per evaluation.  The scalar recursion is written
-// expression by expression in a fixed order because PCL's line search ends on a round-off test: the result
-// is only reproducible when f, df and every scalar step are bit-identical.
+// cost functor, is a kernel.  The scalar recursion is written expression by expression in a fixed order because
+// PCL's line search ends on a round-off test: the result is only reproducible when f, df and every scalar step
+// are bit-identical.
+//
+// Batching: the recursion of ONE scan is a chain of ~100 dependent evaluations, each a few microseconds of device
+// work behind a launch and a read-back — latency, not throughput.  A batch therefore runs every scan's recursion
+// as its own FIBER (ucontext): the unmodified blocking code of one scan runs until it needs an evaluation, posts
+// its request (new correspondences and / or one cost-functor evaluation) and yields; when every live fiber has
+// yielded, the coordinator serves the whole round with one launch per kernel (blockIdx.y = scan), one 14-double
+// read-back per scan and ONE synchronisation, then resumes the fibers.  A scan's arithmetic does not depend on
+// which other scans share its rounds: results are bit-identical to the one-scan-at-a-time path of round 1.
+struct GicpJob;
+void gicp_yield(GicpJob* job);
 
 struct GicpHostFunctor {
   b2icp_handle* h;
   ScanSlot* s;
   GridSlot* g;
+  GicpJob* job = nullptr;
   float base[16];
   long evals = 0;
   int rc = 0;
@@ -80,49 +91,8 @@ struct GicpHostFunctor {
     g[5] = inner(dpsi);
   }
 
-  // one cost-functor evaluation: kernel + D2H of the per-CTA sums + the in-order host sum
-  void fdf(const double* x, double* f, double* g) {
-    ++evals;
-    if (rc) {
-      if (f) *f = 0;
-      if (g) for (int i = 0; i < 6; ++i) g[i] = 0;
-      return;
-    }
-    GicpEvalArgs a;
-    std::memcpy(a.Tx, base, sizeof(base));
-    std::memcpy(a.base, base, sizeof(base));
-    apply_state(a.Tx, x);
-    const int n = (int)s->src.n;
-    const int nblk = (n + kGicpThreads - 1) / kGicpThreads;
-    gicp_fdf_kernel<<<nblk, kGicpThreads, 0, h->stream>>>(s->src.raw.as<float4>(), g_tgt(), n, a, s->corr_idx.as<int>(),
-                                                          s->mahal.as<double>(), s->gicp_partials.as<double>());
-    h->launches += 1;
-    cudaError_t e = cudaMemcpyAsync(h->h_gicp_partials, s->gicp_partials.p, (size_t)nblk * kGicpSums * sizeof(double),
-                                    cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    if (e != cudaSuccess) {
-      rc = B2ICP_ERR_CUDA;
-      h->err = std::string("gicp_fdf_kernel: ") + cudaGetErrorString(e);
-      return;
-    }
-    double S[kGicpSums];
-    for (int k = 0; k < kGicpSums; ++k) {
-      double tot = 0.0;
-      for (int b = 0; b < nblk; ++b) tot += h->h_gicp_partials[(size_t)b * kGicpSums + k];
-      S[k] = tot;
-    }
-    m = (long)S[13];
-    const double md = (double)m;
-    if (f) *f = S[0] / md;
-    if (g) {
-      g[0] = S[1] * 2.0 / md;
-      g[1] = S[2] * 2.0 / md;
-      g[2] = S[3] * 2.0 / md;
-      double R[9];
-      for (int k = 0; k < 9; ++k) R[k] = S[4 + k] * (2.0 / md);
-      compute_r_derivative(x, R, g);
-    }
-  }
+  // one cost-functor evaluation: posted to the batch's round (see GicpJob), answered with the 14 sums
+  void fdf(const double* x, double* f, double* g);
   const float4* g_tgt() const { return g->pts; }
 };
 
@@ -433,7 +403,7 @@ struct GicpBFGS {
     std::memcpy(x0, x, sizeof(x0));
     g0norm = norm(g0);
     pnorm = norm(p);
-    double dir = (dot(p, gradient) > 0) ? -1.0 : 1.0;
+    double dir = (dot(p, gradient) >= 0) ? -1.0 : 1.0;  /* GSL vector_bfgs2: dir = (pg >= 0.0) ? -1.0 : +1.0 */
     for (int i = 0; i < N; ++i) p[i] *= dir / pnorm;
     pnorm = norm(p);
     fp0 = dot(p, g0);
@@ -460,46 +430,67 @@ int compute_covariances(b2icp_handle* h, GridSlot& g, size_t n, DeviceBuf& cov) 
   return B2ICP_OK;
 }
 
-// GICP::computeTransformation for slot 0 (Registration::align around it); fills h->h_states[0].
-int run_gicp(b2icp_handle* h, const float* guess16) {
-  ScanSlot& s = slot(h, 0);
-  GridSlot& g = gslot(h, s.grid);
-  const size_t n = s.src.n;
-  int rc = ensure_slot_work(h, s);
-  if (rc) return rc;
-  CK(s.corr_pos.ensure(n * sizeof(int)));  // sorted position of the last match: the seed of the next search
-  // covariances: target (cached with its grid) and source (own temporary grid)
-  if (!g.cov_valid) {
-    rc = compute_covariances(h, g, (size_t)g.view.n, g.cov);
-    if (rc) return rc;
-    g.cov_valid = true;
-  }
-  {
-    GridSlot& sg = gslot(h, kMaxBatch + 1);
-    sg.pts = s.src.raw.as<float4>();
-    GridSlot* gp = &sg;
-    size_t nn = n;
-    rc = build_grids(h, &gp, &nn, 1);
-    if (rc) return rc;
-    rc = compute_covariances(h, sg, n, s.cov);
-    if (rc) return rc;
-  }
-  const int nblk = (int)((n + kGicpThreads - 1) / kGicpThreads);
-  CK(s.mahal.ensure(n * 9 * sizeof(double)));
-  CK(s.gicp_partials.ensure((size_t)nblk * kGicpSums * sizeof(double)));
-  if (h->h_gicp_partials_cap < (size_t)nblk * kGicpSums) {
-    if (h->h_gicp_partials) cudaFreeHost(h->h_gicp_partials);
-    h->h_gicp_partials = nullptr;
-    h->h_gicp_partials_cap = 0;
-    CK(cudaMallocHost((void**)&h->h_gicp_partials, (size_t)nblk * kGicpSums * sizeof(double) * 2));
-    h->h_gicp_partials_cap = (size_t)nblk * kGicpSums * 2;
-  }
+// One scan of a GICP batch: its slot, its fiber and the request it is blocked on.
+struct GicpJob {
+  b2icp_handle* h = nullptr;
+  int slot_index = 0;
+  float guess[16];
+  // request of the current round
+  bool want_corr = false, want_fdf = false, finished = false;
+  GicpIterArgs iter;
+  GicpEvalArgs eval;
+  double S[kGicpSums];  // answer to want_fdf
+  // outcome
+  IcpState out;
+  int rc = B2ICP_OK;
+  long evals = 0;
+  // fiber
+  ucontext_t ctx, *back = nullptr;
+  std::vector<char> stack;
+};
 
-  float guess[16], T[16], prevT[16];
-  for (int i = 0; i < 16; ++i) {
-    guess[i] = guess16 ? guess16[i] : ((i % 5 == 0) ? 1.f : 0.f);
-    T[i] = (i % 5 == 0) ? 1.f : 0.f;
+void gicp_yield(GicpJob* job) { swapcontext(&job->ctx, job->back); }
+
+void GicpHostFunctor::fdf(const double* x, double* f, double* g) {
+  ++evals;
+  if (rc) {
+    if (f) *f = 0;
+    if (g) for (int i = 0; i < 6; ++i) g[i] = 0;
+    return;
   }
+  std::memcpy(job->eval.Tx, base, sizeof(base));
+  std::memcpy(job->eval.base, base, sizeof(base));
+  apply_state(job->eval.Tx, x);
+  job->want_fdf = true;
+  gicp_yield(job);  // back when the round has been served
+  if (job->rc) {
+    rc = job->rc;
+    if (f) *f = 0;
+    if (g) for (int i = 0; i < 6; ++i) g[i] = 0;
+    return;
+  }
+  const double* S = job->S;
+  m = (long)S[13];
+  const double md = (double)m;
+  if (f) *f = S[0] / md;
+  if (g) {
+    g[0] = S[1] * 2.0 / md;
+    g[1] = S[2] * 2.0 / md;
+    g[2] = S[3] * 2.0 / md;
+    double R[9];
+    for (int k = 0; k < 9; ++k) R[k] = S[4 + k] * (2.0 / md);
+    compute_r_derivative(x, R, g);
+  }
+}
+
+// GICP::computeTransformation of one scan (Registration::align around it), on the scan's fiber.
+void gicp_job_body(GicpJob& job) {
+  b2icp_handle* h = job.h;
+  ScanSlot& s = slot(h, (size_t)job.slot_index);
+  GridSlot& g = gslot(h, s.grid);
+  float* guess = job.guess;
+  float T[16], prevT[16];
+  for (int i = 0; i < 16; ++i) T[i] = (i % 5 == 0) ? 1.f : 0.f;
   std::memcpy(prevT, T, sizeof(T));
   const b2icp_params& p = h->params;
   const double dist_threshold = p.max_correspondence_distance * p.max_correspondence_distance;
@@ -509,12 +500,13 @@ int run_gicp(b2icp_handle* h, const float* guess16) {
   fn.h = h;
   fn.s = &s;
   fn.g = &g;
-  std::memcpy(fn.base, guess, sizeof(guess));
+  fn.job = &job;
+  std::memcpy(fn.base, guess, 16 * sizeof(float));
   const int max_rings = rings_for_bound(h, (double)g.view.cell);
 
   while (!converged) {
-    GicpIterArgs a;
-    std::memcpy(a.guess, guess, sizeof(guess));
+    GicpIterArgs& a = job.iter;
+    std::memcpy(a.guess, guess, 16 * sizeof(float));
     std::memcpy(a.T, T, sizeof(T));
     double TR[16];
     for (int i = 0; i < 4; ++i)
@@ -529,10 +521,7 @@ int run_gicp(b2icp_handle* h, const float* guess16) {
     a.bound2 = h->cfg.bound2;
     a.max_rings = max_rings;
     a.use_seed = iters > 0;
-    gicp_corr_kernel<<<(unsigned)((n + kSweepThreads - 1) / kSweepThreads), kSweepThreads, 0, h->stream>>>(
-        g.view, s.src.raw.as<float4>(), (int)n, a, s.cov.as<double>(), g.cov.as<double>(), s.mahal.as<double>(),
-        s.corr_idx.as<int>(), s.corr_d2.as<float>(), s.corr_pos.as<int>());
-    h->launches += 1;
+    job.want_corr = true;  // served in the same round as the first evaluation below, before it
     std::memcpy(prevT, T, sizeof(T));
     // estimateRigidTransformationBFGS
     double x[6] = {(double)T[3], (double)T[7], (double)T[11], std::atan2((double)T[9], (double)T[10]),
@@ -540,7 +529,10 @@ int run_gicp(b2icp_handle* h, const float* guess16) {
     GicpBFGS bfgs;
     bfgs.fn = &fn;
     bfgs.init(x);  // the first evaluation also counts the correspondences
-    if (fn.rc) return fn.rc;
+    if (fn.rc) {
+      job.rc = fn.rc;
+      break;
+    }
     n_corr = fn.m;
     if (n_corr < 4) {  // NotEnoughPointsException -> break, converged_ stays false
       status = B2ICP_ERR_NOT_ENOUGH_CORRESPONDENCES;
@@ -553,7 +545,10 @@ int run_gicp(b2icp_handle* h, const float* guess16) {
       if (result) break;
       result = bfgs.test_gradient(1e-2);
     } while (result == GicpBFGS::kRunning && inner < p.max_inner_iterations);
-    if (fn.rc) return fn.rc;
+    if (fn.rc) {
+      job.rc = fn.rc;
+      break;
+    }
     if (!(result == GicpBFGS::kNoProgress || result == GicpBFGS::kSuccess || inner == p.max_inner_iterations)) {
       status = B2ICP_ERR_SOLVER_FAILED;
       break;
@@ -574,7 +569,7 @@ int run_gicp(b2icp_handle* h, const float* guess16) {
     }
   }
   // final_transformation_ = previous_transformation_ * guess (Matrix4f product)
-  IcpState& st = h->h_states[0];
+  IcpState& st = job.out;
   std::memset(&st, 0, sizeof(st));
   for (int r = 0; r < 4; ++r)
     for (int c = 0; c < 4; ++c) {
@@ -587,24 +582,215 @@ int run_gicp(b2icp_handle* h, const float* guess16) {
   st.n_corr = (int)n_corr;
   st.status = status;
   st.mse = std::nan("");
-  h->timing.kernel_launches = h->launches;
-  h->gicp_evals = fn.evals;
-  // the device copy of the state feeds b2icp_fitness / the aligned-cloud transform
-  ScanTask& t = h->h_tasks[0];
-  t.grid = g.view;
-  t.src = s.src.raw.as<float4>();
-  t.cur = s.cur.as<float4>();
-  t.corr_idx = s.corr_idx.as<int>();
-  t.corr_d2 = s.corr_d2.as<float>();
-  t.c0 = s.c0.as<float4>();
-  t.c1 = s.c1.as<float4>();
-  t.c2 = s.c2.as<float4>();
-  t.partials = s.partials.as<double>();
-  t.state = h->states.as<IcpState>();
-  t.n = (int)n;
-  t.pad = 0;
-  CK(cudaMemcpyAsync(h->tasks.p, h->h_tasks, sizeof(ScanTask), cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemcpyAsync(h->states.p, h->h_states, sizeof(IcpState), cudaMemcpyHostToDevice, h->stream));
-  CK(cudaStreamSynchronize(h->stream));
-  return B2ICP_OK;
+  job.evals = fn.evals;
 }
+
+thread_local GicpJob* g_entry_job = nullptr;
+void gicp_fiber_entry() {
+  GicpJob* job = g_entry_job;
+  gicp_job_body(*job);
+  job->finished = true;
+  gicp_yield(job);
+}
+
+// GICP::computeTransformation for the scans in slots [0, B): sources uploaded, target grids built.  guesses: B x 16
+// floats or NULL.  Fills h->h_states[0 .. B) and mirrors them (and the tasks getFitnessScore reads) to the device.
+int run_gicp_batch(b2icp_handle* h, int B, const float* guesses) {
+  if (B < 1 || B > kMaxBatch) return fail(h, B2ICP_ERR_INVALID_ARG, "batch too large");
+  // ---- setup per scan: work buffers and covariances (target: cached with its grid; source: own temporary grid)
+  size_t max_n = 0;
+  int setup_rc[kMaxBatch];
+  for (int i = 0; i < B; ++i) {
+    ScanSlot& s = slot(h, (size_t)i);
+    GridSlot& g = gslot(h, s.grid);
+    const size_t n = s.src.n;
+    max_n = std::max(max_n, n);
+    setup_rc[i] = B2ICP_OK;
+    int rc = ensure_slot_work(h, s);
+    if (rc) return rc;
+    CK(s.corr_pos.ensure(n * sizeof(int)));  // sorted position of the last match: the seed of the next search
+    if (!g.cov_valid) {
+      rc = compute_covariances(h, g, (size_t)g.view.n, g.cov);
+      if (rc == B2ICP_ERR_CUDA) return rc;
+      if (rc) {  // e.g. fewer target points than k_correspondences: this scan fails, the batch goes on
+        setup_rc[i] = rc;
+        continue;
+      }
+      g.cov_valid = true;
+    }
+    GridSlot& sg = gslot(h, kMaxBatch + 1);
+    sg.pts = s.src.dev();
+    GridSlot* gp = &sg;
+    size_t nn = n;
+    rc = build_grids(h, &gp, &nn, 1);
+    if (!rc) rc = compute_covariances(h, sg, n, s.cov);
+    if (rc == B2ICP_ERR_CUDA) return rc;
+    if (rc) {
+      setup_rc[i] = rc;
+      continue;
+    }
+    const int nblk = (int)((n + kGicpThreads - 1) / kGicpThreads);
+    CK(s.mahal.ensure(n * 9 * sizeof(double)));
+    CK(s.gicp_partials.ensure(((size_t)nblk + 1) * kGicpSums * sizeof(double)));  // + the scan's 14 sums
+  }
+  // ---- round buffers: task arrays (pinned + device) and the sums that come back
+  const size_t task_bytes = (size_t)B * (sizeof(GicpCorrTask) + sizeof(GicpFdfTask));
+  if (h->h_gicp_tasks_cap < task_bytes) {
+    if (h->h_gicp_tasks) cudaFreeHost(h->h_gicp_tasks);
+    h->h_gicp_tasks = nullptr;
+    h->h_gicp_tasks_cap = 0;
+    CK(cudaMallocHost((void**)&h->h_gicp_tasks, (size_t)kMaxBatch * (sizeof(GicpCorrTask) + sizeof(GicpFdfTask))));
+    h->h_gicp_tasks_cap = (size_t)kMaxBatch * (sizeof(GicpCorrTask) + sizeof(GicpFdfTask));
+  }
+  if (h->h_gicp_partials_cap < (size_t)kMaxBatch * kGicpSums) {
+    if (h->h_gicp_partials) cudaFreeHost(h->h_gicp_partials);
+    h->h_gicp_partials = nullptr;
+    h->h_gicp_partials_cap = 0;
+    CK(cudaMallocHost((void**)&h->h_gicp_partials, (size_t)kMaxBatch * kGicpSums * sizeof(double)));
+    h->h_gicp_partials_cap = (size_t)kMaxBatch * kGicpSums;
+  }
+  CK(h->gicp_tasks.ensure((size_t)kMaxBatch * (sizeof(GicpCorrTask) + sizeof(GicpFdfTask))));
+  GicpCorrTask* h_corr = reinterpret_cast<GicpCorrTask*>(h->h_gicp_tasks);
+  GicpFdfTask* h_fdf = reinterpret_cast<GicpFdfTask*>(h_corr + kMaxBatch);
+  GicpCorrTask* d_corr = h->gicp_tasks.as<GicpCorrTask>();
+  GicpFdfTask* d_fdf = reinterpret_cast<GicpFdfTask*>(d_corr + kMaxBatch);
+
+  // ---- one fiber per scan
+  std::vector<std::unique_ptr<GicpJob>> jobs;
+  ucontext_t main_ctx;
+  for (int i = 0; i < B; ++i) {
+    jobs.emplace_back(new GicpJob());
+    GicpJob& j = *jobs.back();
+    j.h = h;
+    j.slot_index = i;
+    for (int k = 0; k < 16; ++k) j.guess[k] = guesses ? guesses[16 * i + k] : ((k % 5 == 0) ? 1.f : 0.f);
+    if (setup_rc[i]) {  // no fiber: the scan reports its setup failure (PCL: PCL_ERROR and converged_ = false)
+      j.finished = true;
+      j.rc = setup_rc[i];
+      std::memset(&j.out, 0, sizeof(j.out));
+      for (int k = 0; k < 16; ++k) j.out.final_T[k] = j.guess[k];
+      j.out.status = setup_rc[i];
+      j.out.mse = std::nan("");
+      continue;
+    }
+    j.stack.resize(256 * 1024);
+    j.back = &main_ctx;
+    getcontext(&j.ctx);
+    j.ctx.uc_stack.ss_sp = j.stack.data();
+    j.ctx.uc_stack.ss_size = j.stack.size();
+    j.ctx.uc_link = &main_ctx;
+    makecontext(&j.ctx, gicp_fiber_entry, 0);
+  }
+  int live = 0;
+  for (auto& jp : jobs) live += jp->finished ? 0 : 1;
+  long rounds = 0;
+  int rc_round = B2ICP_OK;
+  while (live > 0) {
+    // run every live fiber up to its next request
+    for (auto& jp : jobs) {
+      GicpJob& j = *jp;
+      if (j.finished) continue;
+      j.want_corr = j.want_fdf = false;
+      g_entry_job = &j;
+      swapcontext(&main_ctx, &j.ctx);
+      if (j.finished) --live;
+    }
+    // serve the round: correspondences first, then the evaluations, in stream order
+    int nc = 0, nf = 0;
+    int fdf_of[kMaxBatch];
+    for (int i = 0; i < B; ++i) {
+      GicpJob& j = *jobs[i];
+      if (j.finished) continue;
+      ScanSlot& s = slot(h, (size_t)i);
+      GridSlot& g = gslot(h, s.grid);
+      const int n = (int)s.src.n;
+      if (j.want_corr) {
+        GicpCorrTask& t = h_corr[nc++];
+        t.g = g.view;
+        t.src = s.src.dev();
+        t.cov_src = s.cov.as<double>();
+        t.cov_tgt = g.cov.as<double>();
+        t.mahal = s.mahal.as<double>();
+        t.corr_idx = s.corr_idx.as<int>();
+        t.corr_d2 = s.corr_d2.as<float>();
+        t.corr_pos = s.corr_pos.as<int>();
+        t.n = n;
+        t.pad = 0;
+        t.a = j.iter;
+      }
+      if (j.want_fdf) {
+        const int nblk = (n + kGicpThreads - 1) / kGicpThreads;
+        fdf_of[nf] = i;
+        GicpFdfTask& t = h_fdf[nf++];
+        t.src = s.src.dev();
+        t.tgt = g.pts;
+        t.corr_idx = s.corr_idx.as<int>();
+        t.mahal = s.mahal.as<double>();
+        t.partials = s.gicp_partials.as<double>();
+        t.sums = s.gicp_partials.as<double>() + (size_t)nblk * kGicpSums;
+        t.n = n;
+        t.pad = 0;
+        t.a = j.eval;
+      }
+    }
+    if (nc == 0 && nf == 0) continue;
+    ++rounds;
+    cudaError_t e = cudaSuccess;
+    if (nc) {
+      e = cudaMemcpyAsync(d_corr, h_corr, (size_t)nc * sizeof(GicpCorrTask), cudaMemcpyHostToDevice, h->stream);
+      gicp_corr_kernel<<<dim3((unsigned)((max_n + kSweepThreads - 1) / kSweepThreads), (unsigned)nc, 1), kSweepThreads, 0, h->stream>>>(d_corr);
+      h->launches += 1;
+    }
+    if (nf && e == cudaSuccess) {
+      e = cudaMemcpyAsync(d_fdf, h_fdf, (size_t)nf * sizeof(GicpFdfTask), cudaMemcpyHostToDevice, h->stream);
+      gicp_fdf_kernel<<<dim3((unsigned)((max_n + kGicpThreads - 1) / kGicpThreads), (unsigned)nf, 1), kGicpThreads, 0, h->stream>>>(d_fdf);
+      gicp_sum_kernel<<<nf, 32, 0, h->stream>>>(d_fdf);
+      h->launches += 2;
+      for (int k = 0; k < nf && e == cudaSuccess; ++k)
+        e = cudaMemcpyAsync(h->h_gicp_partials + (size_t)k * kGicpSums, h_fdf[k].sums, kGicpSums * sizeof(double),
+                            cudaMemcpyDeviceToHost, h->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      rc_round = B2ICP_ERR_CUDA;
+      h->err = std::string("GICP round: ") + cudaGetErrorString(e);
+      for (auto& jp : jobs) jp->rc = B2ICP_ERR_CUDA;  // every fiber unwinds at its next evaluation
+    }
+    for (int k = 0; k < nf; ++k) std::memcpy(jobs[fdf_of[k]]->S, h->h_gicp_partials + (size_t)k * kGicpSums, kGicpSums * sizeof(double));
+  }
+  h->gicp_rounds = rounds;
+  h->gicp_evals = 0;
+  int worst = rc_round;
+  for (int i = 0; i < B; ++i) {
+    GicpJob& j = *jobs[i];
+    h->gicp_evals += j.evals;
+    h->h_states[i] = j.out;
+    if (j.rc && worst == B2ICP_OK) worst = j.rc;
+    // the device copy of the state feeds b2icp_fitness / the aligned-cloud transform
+    ScanSlot& s = slot(h, (size_t)i);
+    GridSlot& g = gslot(h, s.grid);
+    ScanTask& t = h->h_tasks[i];
+    t.grid = g.view;
+    t.src = s.src.dev();
+    t.cur = s.cur.as<float4>();
+    t.corr_idx = s.corr_idx.as<int>();
+    t.corr_d2 = s.corr_d2.as<float>();
+    t.c0 = s.c0.as<float4>();
+    t.c1 = s.c1.as<float4>();
+    t.c2 = s.c2.as<float4>();
+    t.partials = s.partials.as<double>();
+    t.state = h->states.as<IcpState>() + i;
+    t.n = (int)s.src.n;
+    t.pad = 0;
+  }
+  h->timing.kernel_launches = h->launches;
+  if (worst == B2ICP_ERR_CUDA) return worst;
+  CK(cudaMemcpyAsync(h->tasks.p, h->h_tasks, sizeof(ScanTask) * B, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->states.p, h->h_states, sizeof(IcpState) * B, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return worst == B2ICP_OK ? B2ICP_OK : worst;
+}
+
+// GICP::computeTransformation for slot 0 (Registration::align around it); fills h->h_states[0].
+int run_gicp(b2icp_handle* h, const float* guess16) { return run_gicp_batch(h, 1, guess16); }

@@ -54,6 +54,9 @@ int b2o_transform_cloud_f(const float* in_xyzw, size_t n, const float* T, float*
 
 /* GICP computeCovariances (Appendix A.2): cov9 = n * 9 doubles, row-major 3x3 per point. */
 int b2o_covariances(const float* xyzw, size_t n, int k, double gicp_epsilon, double* cov9);
+/* tests only: every GICP cost-functor evaluation appends x[6], f, |g| (NaN = not asked for) to buf (8 doubles each) */
+void b2o_gicp_trace(double* buf, size_t cap_records);
+size_t b2o_gicp_trace_count(void);
 
 /* TransformationEstimationSVD / Umeyama on already-matched pairs (Appendix A.3).
  * T16 row-major double (before the cast to float PCL would store). */

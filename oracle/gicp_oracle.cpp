@@ -163,6 +163,11 @@ double tree_sum(const double* v, size_t n) {
   return total;
 }
 
+/* ---- evaluation trace (tests only): every cost-functor evaluation appends x[6], f, |g| (NaN when the value was
+ * not asked for) to a caller's buffer, so that an independent restatement can be compared step by step ------ */
+double* g_trace = nullptr;
+size_t g_trace_cap = 0, g_trace_n = 0;
+
 /* ---- the cost functor (OptimizationFunctorWithIndices) ------------------------------------------ */
 struct Functor {
   const float* src;                  /* `output` = untransformed source, xyzw */
@@ -227,6 +232,13 @@ struct Functor {
       double R[9];
       for (int k = 0; k < 9; ++k) R[k] = S[4 + k] * (2.0 / (double)m);
       compute_r_derivative(x, R, g);
+    }
+    if (g_trace && g_trace_n < g_trace_cap) {
+      double* r = g_trace + 8 * g_trace_n++;
+      for (int k = 0; k < 6; ++k) r[k] = x[k];
+      r[6] = f ? *f : std::numeric_limits<double>::quiet_NaN();
+      r[7] = g ? std::sqrt(g[0] * g[0] + g[1] * g[1] + g[2] * g[2] + g[3] * g[3] + g[4] * g[4] + g[5] * g[5])
+               : std::numeric_limits<double>::quiet_NaN();
     }
   }
 };
@@ -547,7 +559,7 @@ struct BFGS {
     std::memcpy(x0, x, sizeof(x0));
     g0norm = norm(g0);
     pnorm = norm(p);
-    double dir = (dot(p, gradient) > 0) ? -1.0 : 1.0;
+    double dir = (dot(p, gradient) >= 0) ? -1.0 : 1.0;  /* GSL vector_bfgs2: dir = (pg >= 0.0) ? -1.0 : +1.0 */
     for (int i = 0; i < N; ++i) p[i] *= dir / pnorm;
     pnorm = norm(p);
     fp0 = dot(p, g0);
@@ -604,6 +616,13 @@ int compute_covariances(const float* cloud, size_t n, const void* tree, int k, d
 }
 
 }  // namespace
+
+extern "C" void b2o_gicp_trace(double* buf, size_t cap_records) {
+  g_trace = buf;
+  g_trace_cap = buf ? cap_records : 0;
+  g_trace_n = 0;
+}
+extern "C" size_t b2o_gicp_trace_count(void) { return g_trace_n; }
 
 extern "C" int b2o_covariances(const float* xyzw, size_t n, int k, double gicp_epsilon, double* cov9) {
   if (!xyzw || !cov9 || k < 1) return B2ICP_ERR_INVALID_ARG;

@@ -115,6 +115,9 @@ def lib() -> C.CDLL:
         L.b2o_align.argtypes = [C.POINTER(Params), fp, C.c_size_t, fp, C.c_size_t, fp, C.POINTER(Result), fp,
                                 C.c_int, ip, fp, C.POINTER(StageMs)]
         L.b2o_fitness.argtypes = [fp, C.c_size_t, fp, C.c_size_t, fp, C.c_double, dp]
+        L.b2o_gicp_trace.argtypes = [dp, C.c_size_t]
+        L.b2o_gicp_trace.restype = None
+        L.b2o_gicp_trace_count.restype = C.c_size_t
         for f in ("b2o_pose_compose", "b2o_pose_inverse", "b2o_pose_from_matrix"):
             getattr(L, f).restype = None
         L.b2o_pose_compose.argtypes = [dp, dp, dp]
@@ -244,6 +247,19 @@ def align(params: Params, src, tgt, guess=None, want_aligned=False, record_iter=
     return dict(rc=rc, result=res, T=res.matrix(), aligned=aligned, corr_idx=ci, corr_d2=cd,
                 stages={n: getattr(st, n) for n, _ in StageMs._fields_}, iterations=res.iterations,
                 converged=res.converged, n_corr=res.n_corr_last, mse=res.mse_last)
+
+
+def align_gicp_traced(params: Params, src, tgt, cap: int = 20000):
+    """align() in GICP mode with the evaluation trace switched on: returns (align dict, trace[n, 8]) where every row
+    is one cost-functor evaluation: x[0..5], f, |gradient| (NaN = not asked for)."""
+    buf = np.full((cap, 8), np.nan, np.float64)
+    lib().b2o_gicp_trace(_d(buf), cap)
+    try:
+        out = align(params, src, tgt)
+        n = int(lib().b2o_gicp_trace_count())
+    finally:
+        lib().b2o_gicp_trace(None, 0)
+    return out, buf[:n].copy()
 
 
 def fitness(src, tgt, T, max_range=1.7976931348623157e308):

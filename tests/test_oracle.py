@@ -308,3 +308,78 @@ def test_voxel_filter_matches_a_numpy_restatement(oracle):
         ref[:, :3] = sums / counts[:, None].astype(np.float32)
         out = oracle.voxel_filter(cloud, leaf)
         assert out.shape == ref.shape and np.array_equal(out, ref)
+
+
+# ------------------------------------------------------------------------------------------------
+# second witness of the GICP oracle: an independent restatement of the outer loop,
+# the cost functor and GSL's vector_bfgs2 / linear_minimize (tests/gicp_witness.py)
+# ------------------------------------------------------------------------------------------------
+def _witness_case(name):
+    if name == "C1":      # BASELINE configs[0]: 4k-pt sweep pair, odometer budget (10 outer iterations)
+        _, _, sw = synth.sweep_sequence(1, 2, n_beams=64, n_az=64)
+        return sw[1], sw[0], "odometer"
+    _, _, sc = synth.planar_stream(3, 2)  # BASELINE configs[2]: planar 1080-pt scans (rank-2 neighbourhoods)
+    return sc[1], sc[0], "odometer"
+
+
+@pytest.mark.parametrize("case", ["C1", "C3"])
+def test_gicp_oracle_and_independent_witness_evaluate_the_same_sequence(oracle, case):
+    """Every cost-functor evaluation of the whole align — the point x asked for, f and |gradient| — is bit-identical
+    between oracle/gicp_oracle.cpp and tests/gicp_witness.py (numpy + a transcription of GSL's bfgs2 written from
+    SURVEY.md App. A.4, not from the oracle), and so are the iteration count and the final transform.  PCL's line
+    search ends on a round-off test, so two restatements that differed anywhere in the recursion (bracketing,
+    sectioning, cubic / quadratic interpolation, the BFGS direction update, the wrapper's caches, applyState,
+    computeRDerivative, the Mahalanobis algebra) would part ways within a few evaluations."""
+    import gicp_witness as W
+    src, tgt, preset = _witness_case(case)
+    p = oracle.default_params(preset, oracle.MODE_GICP_BFGS)
+    o, trace = oracle.align_gicp_traced(p, src, tgt)
+    assert o["rc"] == 0 and len(trace) > 50
+    w = W.gicp_align(src, tgt, oracle.covariances(src), oracle.covariances(tgt), p.max_iterations)
+    assert w["iterations"] == o["iterations"] and bool(w["converged"]) == bool(o["converged"])
+    assert w["n_corr"] == o["n_corr"]
+    assert w["trace"].shape == trace.shape
+    assert np.array_equal(w["trace"], trace, equal_nan=True)          # x[6], f, |g| of every evaluation
+    assert np.array_equal(w["T"].astype(np.float64), o["T"])
+
+
+def test_gicp_gradient_matches_finite_differences(oracle):
+    """computeRDerivative + the translation part of df against central differences of f (2e-8
+    is achievable for the analytic form; f itself is evaluated on float32-transformed points, which bounds what a
+    finite difference can resolve)."""
+    import gicp_witness as W
+    src, tgt, _ = _witness_case("C1")
+    cs, ct = oracle.covariances(src), oracle.covariances(tgt)
+    tree = cKDTree(tgt[:, :3].astype(np.float64))
+    d, nn = tree.query(src[:, :3].astype(np.float64))
+    keep = d * d < 1.0
+    M = np.tile(np.eye(3), (len(src), 1, 1))
+    M[keep] = W.mahalanobis(np.eye(3), cs[keep], ct[nn[keep]])
+    fn = W.Functor(src.astype(np.float32), tgt.astype(np.float32), np.where(keep, nn, -1), M, np.eye(4, dtype=np.float32))
+    x = [0.02, -0.01, 0.005, 0.004, -0.003, 0.006]
+    _, g = fn.fdf(x)
+    fd = W.finite_difference_gradient(fn, x, h=2e-4)
+    assert np.abs(g - fd).max() <= 2e-3 * max(1.0, np.abs(g).max()), (g, fd)
+
+
+def test_gicp_covariances_match_a_numpy_restatement(oracle):
+    """computeCovariances (k = 20 neighbours, the point included; cov = E[pp^T] - mean mean^T; SVD; singular values
+    -> (1, 1, 1e-3)) against scipy's k-d tree + numpy.  Degenerate neighbourhoods aside (the smallest direction
+    is then implementation-defined) the regularised matrices agree to round-off."""
+    _, _, sw = synth.sweep_sequence(1, 1, n_beams=64, n_az=64)
+    cloud = sw[0]
+    C = oracle.covariances(cloud)
+    xyz = cloud[:, :3].astype(np.float64)
+    _, idx = cKDTree(xyz).query(xyz, k=20)
+    nb32 = cloud[:, :3][idx]                           # [n, 20, 3] float32
+    nb = nb32.astype(np.float64)
+    mean = nb.sum(axis=1) / 20.0
+    # PCL: `cov(k, l) += pt.k * pt.l` — the product is a FLOAT product, the accumulation is double
+    prod = (nb32[:, :, :, None] * nb32[:, :, None, :]).astype(np.float64)
+    cov = prod.sum(axis=1) / 20.0 - np.einsum("ni,nj->nij", mean, mean)
+    U, S, _ = np.linalg.svd(cov)
+    reg = np.einsum("nik,k,njk->nij", U, np.array([1.0, 1.0, 1e-3]), U)
+    gap = (S[:, 1] - S[:, 2]) / np.maximum(S[:, 0], 1e-30)     # well separated smallest direction
+    ok = gap > 1e-3
+    assert ok.mean() > 0.9
+    assert np.abs(C[ok] - reg[ok]).max() < 1e-6
