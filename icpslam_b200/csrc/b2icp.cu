@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -163,6 +164,15 @@ struct b2icp_handle {
   size_t map_size = 0, map_table_cap = 0;
   double map_resolution = 0.0;
   bool map_grid_valid = false;
+  // PCL-compatible map mode (b2icp_map_reset_octree): the root box as PCL grows it, the (level, key) prefix table
+  bool map_compat = false;
+  OctreeBox map_box{};
+  double map_org[3] = {0, 0, 0};
+  DeviceBuf tree_keys, tree_vals, map_first;
+  size_t tree_cap = 0;
+  bool tree_valid = false;
+  int* h_first = nullptr;     // pinned
+  float* h_point = nullptr;   // pinned, one point
   DeviceBuf query, q_idx, q_d2, xf_in, xf_out, mat;
   IcpState* h_states = nullptr;  // pinned [kSlots]: upload (init) and read-back
   ScanTask* h_tasks = nullptr;   // pinned [kSlots]
@@ -978,6 +988,8 @@ int b2icp_create(const b2icp_params* p, b2icp_handle** out) {
             cudaMallocHost((void**)&h->h_states, sizeof(IcpState) * kSlots) == cudaSuccess &&
             cudaMallocHost((void**)&h->h_tasks, sizeof(ScanTask) * kSlots) == cudaSuccess &&
             cudaMallocHost((void**)&h->h_bbox, sizeof(BBox) * (kMaxBatch + 1)) == cudaSuccess &&
+            cudaMallocHost((void**)&h->h_first, sizeof(int)) == cudaSuccess &&
+            cudaMallocHost((void**)&h->h_point, 4 * sizeof(float)) == cudaSuccess &&
             h->states.ensure(sizeof(IcpState) * kSlots) == cudaSuccess &&
             h->tasks.ensure(sizeof(ScanTask) * kSlots) == cudaSuccess &&
             h->unres_count.ensure(sizeof(unsigned int)) == cudaSuccess && h->mat.ensure(16 * sizeof(double)) == cudaSuccess;
@@ -1020,6 +1032,9 @@ int b2icp_destroy(b2icp_handle* h) {
   if (h->h_states) cudaFreeHost(h->h_states);
   if (h->h_tasks) cudaFreeHost(h->h_tasks);
   if (h->h_bbox) cudaFreeHost(h->h_bbox);
+  if (h->h_first) cudaFreeHost(h->h_first);
+  if (h->h_point) cudaFreeHost(h->h_point);
+  for (DeviceBuf* b : {&h->tree_keys, &h->tree_vals, &h->map_first}) b->release();
   if (h->h_gicp_partials) cudaFreeHost(h->h_gicp_partials);
   if (h->h_gicp_tasks) cudaFreeHost(h->h_gicp_tasks);
   h->gicp_tasks.release();
@@ -1494,7 +1509,121 @@ MapTable map_table(b2icp_handle* h) {
   t.vals = h->map_vals.as<int>();
   t.mask = (unsigned int)(h->map_table_cap - 1);
   t.inv_res = 1.0 / h->map_resolution;
+  t.compat = h->map_compat ? 1 : 0;
+  t.res = h->map_resolution;
+  for (int d = 0; d < 3; ++d) t.org[d] = h->map_org[d];
   return t;
+}
+
+// ---- PCL-compatible mode: the root box exactly as pcl::octree::OctreePointCloud grows it ------
+// first point: box = p +- resolution / 2, which getKeyBitSize() widens to a depth-1 tree with the point at its centre
+void octree_define_box(OctreeBox& b, const float* p) {
+  const double res = b.res;
+  const float minValue = FLT_EPSILON;
+  for (int d = 0; d < 3; ++d) {
+    b.mn[d] = (double)p[d] - res / 2;
+    b.mx[d] = (double)p[d] + res / 2;
+  }
+  unsigned mk[3];
+  for (int d = 0; d < 3; ++d) mk[d] = (unsigned)std::ceil((b.mx[d] - b.mn[d] - minValue) / res);
+  const unsigned max_voxels = std::max(std::max(std::max(mk[0], mk[1]), mk[2]), 2u);
+  b.depth = (int)std::max(std::min(32u, (unsigned)std::ceil(std::log((double)max_voxels) / std::log(2.0) - minValue)), 0u);
+  const double side = (double)(1u << b.depth) * res;
+  for (int d = 0; d < 3; ++d) {
+    const double over = (side - (b.mx[d] - b.mn[d])) / 2.0;
+    if (over > minValue) {
+      b.mn[d] -= over;
+      b.mx[d] += over;
+    }
+  }
+  b.defined = 1;
+}
+// adoptBoundingBoxToPoint for a point outside the box: new roots until it fits.  Per axis the old tree becomes the
+// lower child iff that axis' UPPER bound is violated; otherwise the box grows towards minus.
+void octree_grow_box(OctreeBox& b, const float* p) {
+  const float minValue = FLT_EPSILON;
+  for (;;) {
+    bool hi[3], any = false;
+    for (int d = 0; d < 3; ++d) {
+      hi[d] = (double)p[d] >= b.mx[d];
+      any = any || hi[d] || (double)p[d] < b.mn[d];
+    }
+    if (!any) return;
+    double side = (double)(1u << b.depth) * b.res;
+    for (int d = 0; d < 3; ++d)
+      if (!hi[d]) b.mn[d] -= side;
+    b.depth += 1;
+    side = (double)(1u << b.depth) * b.res - minValue;
+    for (int d = 0; d < 3; ++d) b.mx[d] = b.mn[d] + side;
+  }
+}
+
+// smallest index >= cursor of a finite point of pts[0, n) outside the current box (n: none); the point in h->h_point
+int octree_next_outside(b2icp_handle* h, const float4* pts, size_t n, int cursor, int* found) {
+  CK(h->map_first.ensure(sizeof(int)));
+  *h->h_first = INT32_MAX;
+  CK(cudaMemcpyAsync(h->map_first.p, h->h_first, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  const int blocks = (int)std::min<size_t>((n - (size_t)cursor + 255) / 256, 148 * 8);
+  octree_first_outside<<<std::max(blocks, 1), 256, 0, h->stream>>>(pts, (int)n, cursor, h->map_box, h->map_first.as<int>());
+  h->launches += 1;
+  CK(cudaMemcpyAsync(h->h_first, h->map_first.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  *found = *h->h_first;
+  if (*found != INT32_MAX) {
+    CK(cudaMemcpyAsync(h->h_point, pts + *found, 4 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  return B2ICP_OK;
+}
+
+// the (level, key) prefix table of the current map under the current box
+int octree_ensure_tree(b2icp_handle* h) {
+  if (h->tree_valid) return B2ICP_OK;
+  const size_t n = h->map_size;
+  size_t entries = 0, pow8 = 1;
+  for (int level = 1; level <= h->map_box.depth; ++level) {
+    pow8 = pow8 > n ? pow8 : pow8 * 8;
+    entries += std::min(n, pow8);
+  }
+  size_t cap = 1024;
+  while (cap < 2 * entries) cap *= 2;
+  if (cap > (1ull << 31)) return fail(h, B2ICP_ERR_INVALID_ARG, "map too large for the octree table");
+  CK(h->tree_keys.ensure(cap * sizeof(unsigned long long)));
+  CK(h->tree_vals.ensure(cap * sizeof(int)));
+  h->tree_cap = cap;
+  CK(cudaMemsetAsync(h->tree_keys.p, 0xFF, cap * sizeof(unsigned long long), h->stream));
+  CK(cudaMemsetAsync(h->tree_vals.p, 0x7F, cap * sizeof(int), h->stream));
+  MapTable t{};
+  t.keys = h->tree_keys.as<unsigned long long>();
+  t.vals = h->tree_vals.as<int>();
+  t.mask = (unsigned int)(cap - 1);
+  octree_build<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->map_pts.as<float4>(), (int)n, h->map_box, t);
+  h->launches += 1;
+  h->tree_valid = true;
+  return B2ICP_OK;
+}
+
+int map_ensure_grid(b2icp_handle* h);
+
+// the map point OctreeMapper::approxNearestNeighbors pairs with every query: exact nearest neighbour (default), or
+// PCL's greedy octree descent in compat mode
+int map_nearest_impl(b2icp_handle* h, const float4* d_q, size_t n, int* d_idx, float* d_d2) {
+  if (!h->map_compat) {
+    int rc = map_ensure_grid(h);
+    if (rc) return rc;
+    return nn_search_impl(h, d_q, n, d_idx, d_d2, (int)(kMaxBatch + 4));
+  }
+  if (h->map_size == 0) return fail(h, B2ICP_ERR_NO_TARGET, "the map is empty");
+  int rc = octree_ensure_tree(h);
+  if (rc) return rc;
+  MapTable t{};
+  t.keys = h->tree_keys.as<unsigned long long>();
+  t.vals = h->tree_vals.as<int>();
+  t.mask = (unsigned int)(h->tree_cap - 1);
+  octree_approx_nearest<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(d_q, (int)n, h->map_box, t, d_idx);
+  h->launches += 1;
+  (void)d_d2;
+  return B2ICP_OK;
 }
 
 // table able to hold `want` voxels at load <= 0.5; growth re-enters the voxels of the current map
@@ -1560,6 +1689,15 @@ int map_insert_impl(b2icp_handle* h, const float* xyzw, size_t n, bool from_devi
   CK(h->map_slot_of.ensure(n * sizeof(int)));
   CK(h->map_flags.ensure((n + 8) * sizeof(int)));
   const unsigned blocks = (unsigned)((n + 255) / 256);
+  if (h->map_compat && !h->map_box.defined) {  // PCL anchors its lattice on the first point it is given
+    int first = INT32_MAX;
+    rc = octree_next_outside(h, pts, n, 0, &first);
+    if (rc) return rc;
+    if (first == INT32_MAX) return B2ICP_OK;  // no finite point in the cloud
+    octree_define_box(h->map_box, h->h_point);
+    for (int d = 0; d < 3; ++d) h->map_org[d] = h->map_box.mn[d];
+    h->tree_valid = false;
+  }
   const MapTable t = map_table(h);
   map_claim<<<blocks, 256, 0, h->stream>>>(pts, (int)n, t, h->map_slot_of.as<int>());
   map_flag<<<blocks, 256, 0, h->stream>>>((int)n, t, h->map_slot_of.as<int>(), h->map_flags.as<int>());
@@ -1573,7 +1711,20 @@ int map_insert_impl(b2icp_handle* h, const float* xyzw, size_t n, bool from_devi
   CK(cudaGetLastError());
   h->map_size += (size_t)added;
   if (added) h->map_grid_valid = false;
+  if (added) h->tree_valid = false;
   if (n_added) *n_added = (size_t)added;
+  if (h->map_compat) {  // the growth events of this call, in input order: every point outside the box adds roots
+    for (int cursor = 0; cursor < (int)n;) {
+      int first = INT32_MAX;
+      rc = octree_next_outside(h, pts, n, cursor, &first);
+      if (rc) return rc;
+      if (first == INT32_MAX) break;
+      octree_grow_box(h->map_box, h->h_point);
+      if (h->map_box.depth > 19) return fail(h, B2ICP_ERR_INVALID_ARG, "octree deeper than 19 levels");
+      h->tree_valid = false;
+      cursor = first + 1;
+    }
+  }
   return B2ICP_OK;
 }
 
@@ -1591,19 +1742,35 @@ int map_ensure_grid(b2icp_handle* h) {
 }
 }  // namespace
 
-int b2icp_map_reset(b2icp_handle* h, double resolution) {
-  if (!h) return B2ICP_ERR_INVALID_ARG;
-  std::lock_guard<std::mutex> lk(h->mu);
-  CK(cudaSetDevice(h->device));
+static int map_reset_impl(b2icp_handle* h, double resolution, bool compat) {
   if (!(resolution > 0) || !std::isfinite(resolution)) return fail(h, B2ICP_ERR_INVALID_ARG, "resolution must be > 0");
   h->map_resolution = resolution;
   h->map_size = 0;
   h->map_grid_valid = false;
+  h->map_compat = compat;
+  std::memset(&h->map_box, 0, sizeof(h->map_box));
+  h->map_box.res = resolution;
+  h->map_org[0] = h->map_org[1] = h->map_org[2] = 0.0;
+  h->tree_valid = false;
   if (h->map_table_cap) {
     CK(cudaMemsetAsync(h->map_keys.p, 0xFF, h->map_table_cap * sizeof(unsigned long long), h->stream));
     CK(cudaMemsetAsync(h->map_vals.p, 0x7F, h->map_table_cap * sizeof(int), h->stream));
   }
   return B2ICP_OK;
+}
+
+int b2icp_map_reset(b2icp_handle* h, double resolution) {
+  if (!h) return B2ICP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CK(cudaSetDevice(h->device));
+  return map_reset_impl(h, resolution, false);
+}
+
+int b2icp_map_reset_octree(b2icp_handle* h, double resolution) {
+  if (!h) return B2ICP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CK(cudaSetDevice(h->device));
+  return map_reset_impl(h, resolution, true);
 }
 
 int b2icp_map_insert(b2icp_handle* h, const float* xyzw, size_t n, size_t* n_added) {
@@ -1646,13 +1813,12 @@ int b2icp_map_nearest(b2icp_handle* h, const float* q_xyzw, size_t n, int32_t* i
   if (n_nn) *n_nn = 0;
   if (n == 0) return B2ICP_OK;
   if (!q_xyzw) return fail(h, B2ICP_ERR_INVALID_ARG, "q_xyzw == NULL");
-  int rc = map_ensure_grid(h);
-  if (rc) return rc;
+  if (h->map_size == 0) return fail(h, B2ICP_ERR_NO_TARGET, "the map is empty");
   CK(h->query.ensure(n * sizeof(float4)));
   CK(h->q_idx.ensure((n + 8) * sizeof(int)));
   CK(h->q_d2.ensure(n * sizeof(float)));
   CK(cudaMemcpyAsync(h->query.p, q_xyzw, n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
-  rc = nn_search_impl(h, h->query.as<float4>(), n, h->q_idx.as<int>(), h->q_d2.as<float>(), (int)kMapGrid);
+  int rc = map_nearest_impl(h, h->query.as<float4>(), n, h->q_idx.as<int>(), h->q_d2.as<float>());
   if (rc) return rc;
   if (idx) CK(cudaMemcpyAsync(idx, h->q_idx.p, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   if (nn_xyzw) {
@@ -1690,8 +1856,6 @@ int b2icp_mapper_register(b2icp_handle* h, const float* xyzw, size_t n, const fl
   s.grid = 0;
   int rc = upload_cloud(h, s.src, xyzw, n, false);  // icp.setInputSource(curr_cloud), kept for b2icp_mapper_grow
   if (rc) return rc;
-  rc = map_ensure_grid(h);
-  if (rc) return rc;
   const unsigned blocks = (unsigned)((n + 255) / 256);
   CK(h->query.ensure(n * sizeof(float4)));
   CK(h->q_idx.ensure((n + 8) * sizeof(int)));
@@ -1705,7 +1869,7 @@ int b2icp_mapper_register(b2icp_handle* h, const float* xyzw, size_t n, const fl
   // line 136: cloud_in_map = raw_pose (x) cloud
   transform_cloud_f<<<blocks, 256, 0, h->stream>>>(s.src.raw.as<float4>(), (int)n, h->mat.as<float>(), h->query.as<float4>());
   // lines 145 / 73-90: the map point nearest to every scan point, compacted in scan order
-  rc = nn_search_impl(h, h->query.as<float4>(), n, h->q_idx.as<int>(), h->q_d2.as<float>(), (int)kMapGrid);
+  rc = map_nearest_impl(h, h->query.as<float4>(), n, h->q_idx.as<int>(), h->q_d2.as<float>());
   if (rc) return rc;
   map_gather_flag<<<blocks, 256, 0, h->stream>>>(h->q_idx.as<int>(), (int)n, h->map_flags.as<int>());
   int found = 0;

@@ -597,6 +597,12 @@ void gicp_fiber_entry() {
 // floats or NULL.  Fills h->h_states[0 .. B) and mirrors them (and the tasks getFitnessScore reads) to the device.
 int run_gicp_batch(b2icp_handle* h, int B, const float* guesses) {
   if (B < 1 || B > kMaxBatch) return fail(h, B2ICP_ERR_INVALID_ARG, "batch too large");
+  const bool dbg = getenv("B2ICP_GICP_DEBUG") != nullptr;  // tuning only: host wall time of the phases
+  auto now = [] { return std::chrono::steady_clock::now(); };
+  auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+    return std::chrono::duration<double, std::milli>(b - a).count();
+  };
+  const auto t_start = now();
   // ---- setup per scan: work buffers and covariances (target: cached with its grid; source: own temporary grid)
   size_t max_n = 0;
   int setup_rc[kMaxBatch];
@@ -633,6 +639,8 @@ int run_gicp_batch(b2icp_handle* h, int B, const float* guesses) {
     CK(s.mahal.ensure(n * 9 * sizeof(double)));
     CK(s.gicp_partials.ensure(((size_t)nblk + 1) * kGicpSums * sizeof(double)));  // + the scan's 14 sums
   }
+  if (dbg) cudaStreamSynchronize(h->stream);
+  const auto t_setup = now();
   // ---- round buffers: task arrays (pinned + device) and the sums that come back
   const size_t task_bytes = (size_t)B * (sizeof(GicpCorrTask) + sizeof(GicpFdfTask));
   if (h->h_gicp_tasks_cap < task_bytes) {
@@ -759,6 +767,9 @@ int run_gicp_batch(b2icp_handle* h, int B, const float* guesses) {
     }
     for (int k = 0; k < nf; ++k) std::memcpy(jobs[fdf_of[k]]->S, h->h_gicp_partials + (size_t)k * kGicpSums, kGicpSums * sizeof(double));
   }
+  if (dbg)
+    fprintf(stderr, "[b2icp] GICP batch of %d: setup (grids + covariances) %.2f ms, %ld rounds %.2f ms\n", B,
+            ms(t_start, t_setup), rounds, ms(t_setup, now()));
   h->gicp_rounds = rounds;
   h->gicp_evals = 0;
   int worst = rc_round;

@@ -100,7 +100,7 @@ EXPORTS = [
     "b2icp_set_stream", "b2icp_compute_covariances", "b2icp_voxel_filter", "b2icp_get_timing",
     "b2icp_align_batch_submit", "b2icp_align_batch_submit_device", "b2icp_align_batch_wait",
     "b2icp_set_record_sink", "b2icp_record_sink_count",
-    "b2icp_map_reset", "b2icp_map_insert", "b2icp_map_insert_device", "b2icp_map_size", "b2icp_map_download",
+    "b2icp_map_reset", "b2icp_map_reset_octree", "b2icp_map_insert", "b2icp_map_insert_device", "b2icp_map_size", "b2icp_map_download",
     "b2icp_map_nearest", "b2icp_set_target_map", "b2icp_mapper_register", "b2icp_mapper_grow",
     "b2icp_get_grid_info", "b2icp_host_alloc", "b2icp_host_free", "b2icp_last_error", "b2icp_status_string",
     "b2icp_version",
@@ -150,6 +150,7 @@ def load_library() -> C.CDLL:
     L.b2icp_set_record_sink.argtypes = [vp, vp, C.c_size_t]
     L.b2icp_record_sink_count.argtypes = [vp, szp]
     L.b2icp_map_reset.argtypes = [vp, C.c_double]
+    L.b2icp_map_reset_octree.argtypes = [vp, C.c_double]
     L.b2icp_map_insert.argtypes = [vp, vp, C.c_size_t, szp]
     L.b2icp_map_insert_device.argtypes = [vp, vp, C.c_size_t, szp]
     L.b2icp_map_size.argtypes = [vp, szp]
@@ -440,9 +441,12 @@ class Registration:
         return out[: n_out.value].copy()
 
     # ---- OctreeMapper's point map (reference src/icpslam/octree_mapper.cpp:56-90), device-resident
-    def resetMap(self, resolution: float):
-        """OctreeMapper::resetMap."""
-        self._check(self._L.b2icp_map_reset(self._h, float(resolution)), "map_reset")
+    def resetMap(self, resolution: float, pcl_octree: bool = False):
+        """OctreeMapper::resetMap.  pcl_octree=True: PCL-compatible mode (b2icp_map_reset_octree): the lattice is
+        anchored on the first point, the root box grows as PCL's does, approxNearestNeighbors is PCL's greedy
+        octree descent instead of the exact nearest neighbour."""
+        fn = self._L.b2icp_map_reset_octree if pcl_octree else self._L.b2icp_map_reset
+        self._check(fn(self._h, float(resolution)), "map_reset")
 
     def addPointsToMap(self, cloud) -> int:
         """OctreeMapper::addPointsToMap: one point per voxel, first come wins; returns the points added."""

@@ -244,6 +244,15 @@ int b2icp_record_sink_count(b2icp_handle* h, size_t* n);
  *                          localisation without the gather (BASELINE configs[1] and [4]).
  * The map lives in device memory; download / size are for the caller's bookkeeping and publishing. */
 int b2icp_map_reset(b2icp_handle* h, double resolution);
+/* PCL-COMPATIBLE map mode ("offer two NN modes"): like b2icp_map_reset, but the map then
+ * behaves as pcl::octree::OctreePointCloudSearch does in OctreeMapper (octree_mapper.cpp:56-90):
+ *   - voxels are the leaves of PCL's octree: a lattice anchored on the FIRST point inserted (its corner is that
+ *     point minus one resolution), not the global lattice floor(p / resolution);
+ *   - the root box grows as PCL grows it (new roots towards the violated bounds), tracked exactly;
+ *   - b2icp_map_nearest / b2icp_mapper_register pair every query with the map point of the leaf that PCL's
+ *     approxNearestSearch reaches — the greedy descent by voxel-centre distance, NOT the nearest neighbour —
+ *     so that nn_cloud is the reference's nn_cloud.  Exact mode (b2icp_map_reset) stays the default. */
+int b2icp_map_reset_octree(b2icp_handle* h, double resolution);
 int b2icp_map_insert(b2icp_handle* h, const float* xyzw, size_t n, size_t* n_added);
 int b2icp_map_insert_device(b2icp_handle* h, const float* d_xyzw, size_t n, size_t* n_added);
 int b2icp_map_size(b2icp_handle* h, size_t* n);

@@ -90,6 +90,15 @@ void b2o_pose_compose(const double* a7, const double* b7, double* out7);
 void b2o_pose_inverse(const double* a7, double* out7);
 void b2o_pose_from_matrix(const double* T16, double* out7);
 
+/* pcl::octree::OctreePointCloudSearch as OctreeMapper uses it (octree_oracle.cpp) */
+void* b2o_octree_create(double resolution);
+void b2o_octree_free(void* tree);
+size_t b2o_octree_add_points(void* tree, const float* xyzw, size_t n);
+size_t b2o_octree_size(void* tree);
+void b2o_octree_points(void* tree, float* out_xyzw);
+void b2o_octree_box(void* tree, double* min3, int* depth);
+void b2o_octree_approx_nearest(void* tree, const float* q_xyzw, size_t n, int key_rule, int32_t* idx);
+
 #ifdef __cplusplus
 }
 #endif

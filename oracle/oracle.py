@@ -79,7 +79,7 @@ def default_params(preset: str = "odometer", mode: int = MODE_P2P_SVD) -> Params
 
 def build(force: bool = False) -> str:
     """Compile the oracle with the committed recipe (oracle/Makefile)."""
-    srcs = [os.path.join(_HERE, f) for f in ("b2icp_oracle.cpp", "gicp_oracle.cpp", "b2icp_oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("b2icp_oracle.cpp", "gicp_oracle.cpp", "octree_oracle.cpp", "b2icp_oracle.h")]
     stale = (not os.path.exists(_LIB_PATH)) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs if os.path.exists(s))
     if force or stale:
@@ -115,6 +115,20 @@ def lib() -> C.CDLL:
         L.b2o_align.argtypes = [C.POINTER(Params), fp, C.c_size_t, fp, C.c_size_t, fp, C.POINTER(Result), fp,
                                 C.c_int, ip, fp, C.POINTER(StageMs)]
         L.b2o_fitness.argtypes = [fp, C.c_size_t, fp, C.c_size_t, fp, C.c_double, dp]
+        L.b2o_octree_create.restype = C.c_void_p
+        L.b2o_octree_create.argtypes = [C.c_double]
+        L.b2o_octree_free.argtypes = [C.c_void_p]
+        L.b2o_octree_free.restype = None
+        L.b2o_octree_add_points.argtypes = [C.c_void_p, fp, C.c_size_t]
+        L.b2o_octree_add_points.restype = C.c_size_t
+        L.b2o_octree_size.argtypes = [C.c_void_p]
+        L.b2o_octree_size.restype = C.c_size_t
+        L.b2o_octree_points.argtypes = [C.c_void_p, fp]
+        L.b2o_octree_points.restype = None
+        L.b2o_octree_box.argtypes = [C.c_void_p, dp, C.POINTER(C.c_int)]
+        L.b2o_octree_box.restype = None
+        L.b2o_octree_approx_nearest.argtypes = [C.c_void_p, fp, C.c_size_t, C.c_int, ip]
+        L.b2o_octree_approx_nearest.restype = None
         L.b2o_gicp_trace.argtypes = [dp, C.c_size_t]
         L.b2o_gicp_trace.restype = None
         L.b2o_gicp_trace_count.restype = C.c_size_t
@@ -296,6 +310,48 @@ def map_insert(map_cloud, cloud, resolution: float) -> np.ndarray:
     if rc != 0:
         raise RuntimeError(f"b2o_map_insert rc={rc}")
     return out[: n_out.value].copy()
+
+
+class CompatOctree:
+    """pcl::octree::OctreePointCloudSearch as OctreeMapper uses it (oracle/octree_oracle.cpp; SURVEY.md App. A.7):
+    resetMap / addPointsToMap / approxNearestNeighbors with PCL's first-point-anchored, root-growing lattice and its
+    greedy centre-distance descent.  key_rule 0 = PCL 1.8.x literal, 1 = the chosen child's key is handed down."""
+
+    def __init__(self, resolution: float):
+        self._t = lib().b2o_octree_create(float(resolution))
+        if not self._t:
+            raise ValueError("resolution must be > 0")
+
+    def __del__(self):
+        if getattr(self, "_t", None):
+            lib().b2o_octree_free(self._t)
+            self._t = None
+
+    def add_points(self, cloud) -> int:
+        cloud = _cloud(cloud)
+        return int(lib().b2o_octree_add_points(self._t, _f(cloud), len(cloud))) if len(cloud) else 0
+
+    def size(self) -> int:
+        return int(lib().b2o_octree_size(self._t))
+
+    def points(self) -> np.ndarray:
+        out = np.zeros((self.size(), 4), np.float32)
+        if len(out):
+            lib().b2o_octree_points(self._t, _f(out))
+        return out
+
+    def box(self):
+        mn = np.zeros(3)
+        depth = C.c_int()
+        lib().b2o_octree_box(self._t, _d(mn), C.byref(depth))
+        return mn, depth.value
+
+    def approx_nearest(self, q, key_rule: int = 0) -> np.ndarray:
+        q = _cloud(q)
+        idx = np.full(len(q), -1, np.int32)
+        if len(q):
+            lib().b2o_octree_approx_nearest(self._t, _f(q), len(q), key_rule, _i(idx))
+        return idx
 
 
 def pose_compose(a, b):

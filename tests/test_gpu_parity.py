@@ -608,3 +608,52 @@ def test_device_resident_mapper_refine_equals_the_step_by_step_path(R, oracle):
         Tf = (poses[k - 1] @ res.matrix()).astype(np.float32)
         assert fused.mapperGrow(Tf) == steps.addPointsToMap(steps.transformPointCloud(sw[k], Tf, double=False))
     assert np.array_equal(fused.mapCloud(), steps.mapCloud())
+
+
+@pytest.mark.gpu
+def test_pcl_compat_octree_map_mode_matches_the_oracle(R, oracle):
+    """b2icp_map_reset_octree (the PCL-compatible NN mode): lattice anchored on the first point,
+    root box grown as pcl::octree grows it, approxNearestNeighbors = PCL's greedy centre-distance descent.  The map
+    contents and nn_cloud equal the oracle's restatement (oracle/octree_oracle.cpp), duplicates included; the exact
+    mode stays the default and differs."""
+    _, poses, sw = synth.sweep_sequence(11, 4, n_beams=64, n_az=256)
+    reg = R.Registration(preset=R.PRESET_MAPPER)
+    reg.resetMap(0.2, pcl_octree=True)
+    tree = oracle.CompatOctree(0.2)
+    clouds = []
+    for k in range(3):       # sweeps moved into the map frame: the box has to grow in several directions
+        T = poses[k]
+        w = synth.as_xyzw(sw[k][:, :3].astype(np.float64) @ T[:3, :3].T + T[:3, 3])
+        clouds.append(w)
+        assert reg.addPointsToMap(w) == tree.add_points(w)
+    far = synth.as_xyzw(np.array([[-400.0, 30, 2], [500.0, -300, 40], [1.0, 2, -90]]))   # roots added towards - and +
+    assert reg.addPointsToMap(far) == tree.add_points(far)
+    m = reg.mapCloud()
+    assert np.array_equal(m, tree.points())                       # same points, same (scan) order
+    q = synth.as_xyzw(sw[3][:, :3].astype(np.float64) @ poses[3][:3, :3].T + poses[3][:3, 3])
+    idx, nn = reg.approxNearestNeighbors(q)
+    oi = tree.approx_nearest(q, key_rule=1)
+    assert np.array_equal(idx, oi)                                # PCL's approxNearestSearch, index for index
+    assert np.array_equal(nn, m[oi])                              # nn_cloud: map points in query order, duplicates kept
+    assert len(np.unique(oi)) < len(oi)
+    exact, _ = oracle.nn_brute(m, q)
+    assert 0.3 < (oi == exact).mean() < 0.95                      # a greedy descent, not the nearest neighbour
+    # the lattice really is PCL's: the exact-mode map (global lattice) holds a different set of points
+    reg2 = R.Registration(preset=R.PRESET_MAPPER)
+    reg2.resetMap(0.2)
+    for w in clouds:
+        reg2.addPointsToMap(w)
+    reg2.addPointsToMap(far)
+    assert not np.array_equal(reg2.mapCloud(), m)
+    # refineTransformAndGrowMap on the compat map: the fused device path equals the step-by-step calls
+    Tr = poses[2].astype(np.float32)
+    Tri = np.linalg.inv(poses[2]).astype(np.float32)
+    res = reg.mapperRegister(sw[3], Tr, Tri)
+    cim = reg.transformPointCloud(sw[3], Tr, double=False)
+    _, nn_in_map = reg.approxNearestNeighbors(cim)
+    nn_cloud = reg.transformPointCloud(nn_in_map, Tri, double=False)
+    icp = R.Registration(preset=R.PRESET_MAPPER)
+    icp.setInputSource(sw[3])
+    icp.setInputTarget(nn_cloud)
+    icp.align()
+    assert np.array_equal(res.matrix(), icp.getFinalTransformation()) and res.iterations == icp.iterations

@@ -383,3 +383,39 @@ def test_gicp_covariances_match_a_numpy_restatement(oracle):
     ok = gap > 1e-3
     assert ok.mean() > 0.9
     assert np.abs(C[ok] - reg[ok]).max() < 1e-6
+
+
+def test_compat_octree_restatement_properties(oracle):
+    """oracle/octree_oracle.cpp (pcl::octree as OctreeMapper uses it, SURVEY.md App. A.7) against what its rules
+    imply: one point per voxel of the lattice anchored at (first point - resolution), first come wins, in scan order
+    — checked with a numpy restatement; the box grows by new roots; approxNearestSearch returns the point of an
+    occupied leaf, is exact for a query sitting on a map point, and is NOT the nearest neighbour in general."""
+    _, _, sw = synth.sweep_sequence(9, 3, n_beams=64, n_az=256)
+    res = 0.2
+    t = oracle.CompatOctree(res)
+    added = [t.add_points(sw[0]), t.add_points(sw[1])]
+    m = t.points()
+    allp = np.concatenate([sw[0], sw[1]])
+    p0 = sw[0][0, :3].astype(np.float64)
+    org = p0 - res / 2 - res / 2
+    key = np.floor((allp[:, :3].astype(np.float64) - org) / res).astype(np.int64)
+    _, first = np.unique(key, axis=0, return_index=True)
+    first.sort()
+    assert sum(added) == len(first) == t.size() and np.array_equal(allp[first], m)
+    assert t.add_points(sw[0]) == 0                                   # every voxel of sweep 0 is taken
+    mn0, d0 = t.box()
+    far = synth.as_xyzw(np.array([[900.0, 0, 0]]))
+    assert t.add_points(far) == 1
+    mn1, d1 = t.box()
+    k = (mn0 - mn1) / res
+    assert d1 > d0 and mn1[0] == mn0[0] and mn1[1] <= mn0[1] and np.abs(k - np.round(k)).max() < 1e-6   # roots added towards +x only
+    idx = t.approx_nearest(sw[2], key_rule=1)
+    assert idx.min() >= 0 and idx.max() < t.size()
+    on_map = t.approx_nearest(m[::97], key_rule=1)
+    assert np.array_equal(on_map, np.arange(t.size())[::97])          # a query on a map point finds that point
+    exact, _ = oracle.nn_brute(t.points(), sw[2])
+    assert 0.3 < (idx == exact).mean() < 0.95
+    # the literal-1.8 key rule (last child's key handed down) cannot be what ran in the reference's experiments
+    bad = t.approx_nearest(sw[2][:2000], key_rule=0)
+    mm = t.points()
+    assert np.linalg.norm(mm[bad, :3] - sw[2][:2000, :3], axis=1).mean() > 20 * np.linalg.norm(mm[idx[:2000], :3] - sw[2][:2000, :3], axis=1).mean()
