@@ -115,6 +115,24 @@ struct ScanSlot {
 
 __global__ void zero_counter(unsigned int* c) { *c = 0; }
 
+// pcl::fromROSMsg for PointXYZ: the three float fields of every point of a PointCloud2 payload (byte-wise loads: the
+// offsets of a message need not be 4-byte aligned)
+__global__ void __launch_bounds__(256) unpack_pointcloud2(const unsigned char* __restrict__ data, unsigned int width, unsigned int height,
+                                                          unsigned int point_step, unsigned int row_step, unsigned int off_x,
+                                                          unsigned int off_y, unsigned int off_z, int swap, float4* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)width * height) return;
+  const size_t row = i / width, col = i - row * width;
+  const unsigned char* p = data + row * row_step + col * point_step;
+  auto field = [&](unsigned int off) {
+    const unsigned char* b = p + off;
+    const unsigned int v = swap ? ((unsigned int)b[0] << 24) | ((unsigned int)b[1] << 16) | ((unsigned int)b[2] << 8) | b[3]
+                                : ((unsigned int)b[3] << 24) | ((unsigned int)b[2] << 16) | ((unsigned int)b[1] << 8) | b[0];
+    return __uint_as_float(v);
+  };
+  out[i] = make_float4(field(off_x), field(off_y), field(off_z), 1.0f);
+}
+
 // IcpState[B] -> b2icp_record[B] (the record sink of streamed batches: b2icp_set_record_sink)
 __global__ void export_records(const IcpState* __restrict__ st, int B, int with_fitness, b2icp_record* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1934,6 +1952,31 @@ int b2icp_set_target_map(b2icp_handle* h) {
   CK(cudaSetDevice(h->device));
   if (h->map_size == 0) return fail(h, B2ICP_ERR_NO_TARGET, "the map is empty");
   return set_target_impl(h, 0, h->map_pts.as<float>(), h->map_size, true);
+}
+
+int b2icp_pointcloud2_to_xyzw(b2icp_handle* h, const uint8_t* data, size_t data_bytes, uint32_t width, uint32_t height,
+                              uint32_t point_step, uint32_t row_step, uint32_t off_x, uint32_t off_y, uint32_t off_z,
+                              int is_bigendian, float* out_xyzw) {
+  if (!h) return B2ICP_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  CK(cudaSetDevice(h->device));
+  const size_t n = (size_t)width * height;
+  if (n == 0) return B2ICP_OK;
+  if (!data || !out_xyzw) return fail(h, B2ICP_ERR_INVALID_ARG, "pointcloud2: NULL argument");
+  const uint32_t last = std::max(off_x, std::max(off_y, off_z)) + 4;
+  if (point_step < last || (size_t)row_step < (size_t)width * point_step || data_bytes < (size_t)height * row_step)
+    return fail(h, B2ICP_ERR_INVALID_ARG, "pointcloud2: steps / offsets do not fit the payload");
+  if (n > (size_t)INT32_MAX / 8) return fail(h, B2ICP_ERR_INVALID_ARG, "cloud too large");
+  CK(h->xf_in.ensure(data_bytes));
+  CK(h->xf_out.ensure(n * sizeof(float4)));
+  CK(cudaMemcpyAsync(h->xf_in.p, data, data_bytes, cudaMemcpyHostToDevice, h->stream));
+  unpack_pointcloud2<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->xf_in.as<unsigned char>(), width, height, point_step, row_step,
+                                                                         off_x, off_y, off_z, is_bigendian ? 1 : 0, h->xf_out.as<float4>());
+  h->launches += 1;
+  CK(cudaMemcpyAsync(out_xyzw, h->xf_out.p, n * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  CK(cudaGetLastError());
+  return B2ICP_OK;
 }
 
 int b2icp_get_timing(b2icp_handle* h, b2icp_timing* out) {

@@ -102,7 +102,7 @@ EXPORTS = [
     "b2icp_set_record_sink", "b2icp_record_sink_count",
     "b2icp_map_reset", "b2icp_map_reset_octree", "b2icp_map_insert", "b2icp_map_insert_device", "b2icp_map_size", "b2icp_map_download",
     "b2icp_map_nearest", "b2icp_set_target_map", "b2icp_mapper_register", "b2icp_mapper_grow",
-    "b2icp_get_grid_info", "b2icp_host_alloc", "b2icp_host_free", "b2icp_last_error", "b2icp_status_string",
+    "b2icp_pointcloud2_to_xyzw", "b2icp_get_grid_info", "b2icp_host_alloc", "b2icp_host_free", "b2icp_last_error", "b2icp_status_string",
     "b2icp_version",
 ]
 
@@ -159,6 +159,8 @@ def load_library() -> C.CDLL:
     L.b2icp_set_target_map.argtypes = [vp]
     L.b2icp_mapper_register.argtypes = [vp, vp, C.c_size_t, vp, vp, C.POINTER(Result)]
     L.b2icp_mapper_grow.argtypes = [vp, vp, C.c_size_t, vp, szp]
+    L.b2icp_pointcloud2_to_xyzw.argtypes = [vp, vp, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                            C.c_uint32, C.c_uint32, C.c_int, vp]
     L.b2icp_get_timing.argtypes = [vp, C.POINTER(Timing)]
     L.b2icp_get_grid_info.argtypes = [vp, fp, ip, dp]
     L.b2icp_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
@@ -404,6 +406,17 @@ class Registration:
         rc = self._L.b2icp_align_batch_wait(self._h, res, n, C.byref(got))
         self._inflight = pend[1:]
         return rc, list(res)[: got.value]
+
+    def fromROSMsg(self, data: bytes, width: int, height: int, point_step: int, row_step: int, offsets=(0, 4, 8),
+                   is_bigendian: bool = False) -> np.ndarray:
+        """pcl::fromROSMsg for PointXYZ (icp_odometer.cpp:168,173): the payload of a sensor_msgs/PointCloud2 ->
+        float32[width * height, 4]."""
+        buf = np.frombuffer(bytes(data), dtype=np.uint8)
+        out = np.empty((width * height, 4), np.float32)
+        self._check(self._L.b2icp_pointcloud2_to_xyzw(self._h, _ptr(buf) if len(buf) else None, len(buf), width, height, point_step,
+                                                      row_step, offsets[0], offsets[1], offsets[2], 1 if is_bigendian else 0,
+                                                      _ptr(out) if len(out) else None), "pointcloud2_to_xyzw")
+        return out
 
     def setRecordSink(self, device_ptr, capacity: int) -> None:
         """b2icp_set_record_sink: streamed batches append one 96-byte b2icp_record per scan at `device_ptr`

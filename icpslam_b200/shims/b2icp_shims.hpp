@@ -16,9 +16,11 @@
 // Every registration, transform, filter, map operation and search below is a call of the C ABI: there is no CPU
 // path.  The map of OctreeMapper (pcl::octree in the reference) lives in device memory behind b2icp_map_*
 // (csrc/map.cuh): one point per voxel, first come wins, scan order kept; neighbours come from the engine's EXACT
-// search (documented deviation from PCL's greedy approxNearestSearch: never farther than PCL's answer), and
-// refineTransformAndGrowMap uploads the scan once and keeps every intermediate cloud on the device
-// (b2icp_mapper_register / b2icp_mapper_grow).
+// search by default (never farther than PCL's answer) or, with OctreeMapperParams::pcl_octree, from a restatement
+// of PCL's greedy approxNearestSearch on PCL's own lattice; refineTransformAndGrowMap uploads the scan once and
+// keeps every intermediate cloud on the device (b2icp_mapper_register / b2icp_mapper_grow).
+// Both classes default to the estimator the reference instantiates (GICP); mode = B2ICP_MODE_P2P_SVD selects the
+// point-to-point pipeline of the north star.  b2icp_ros_adapter.hpp restores the original ROS signatures.
 #pragma once
 #include <cmath>
 #include <cstdint>
@@ -172,7 +174,10 @@ struct IcpOdometerParams {
   int num_clouds_skip = 0;        // icp_odometer.cpp:45
   double voxel_leaf_size = 0.05;  // icp_odometer.cpp:46 (YAML: 0.2); <= 0 disables the filter
   int verbosity_level = 1;
-  int mode = B2ICP_MODE_P2P_SVD;  // B2ICP_MODE_GICP_BFGS = what the reference instantiates
+  // The estimator.  Default = what the reference instantiates (pcl::GeneralizedIterativeClosestPoint,
+  // icp_odometer.cpp:188): a node that links the shims gets the reference's estimator.  B2ICP_MODE_P2P_SVD is the
+  // north-star point-to-point pipeline: ~20x the throughput, a different answer.
+  int mode = B2ICP_MODE_GICP_BFGS;
   int device = 0;
 };
 
@@ -190,6 +195,7 @@ class IcpOdometer {
   void advertisePublishers() {}   // ROS topics: out of scope
   void registerSubscribers() {}
 
+  b2icp_handle* engine() const { return engine_.get(); }
   bool isOdomReady() const { return odom_inited_; }
   void setInitialPose(const Pose6DOF& initial_pose) { icp_odom_poses_.push_back(initial_pose); initial_pose_set_ = true; }
   Pose6DOF getFirstPose() const { return icp_odom_poses_.front(); }
@@ -275,7 +281,11 @@ class IcpOdometer {
 struct OctreeMapperParams {
   double octree_resolution = 0.5;  // octree_mapper.cpp:42 (YAML: 0.2)
   int verbosity_level = 1;
-  int mode = B2ICP_MODE_P2P_SVD;
+  int mode = B2ICP_MODE_GICP_BFGS;  // octree_mapper.cpp:104 instantiates GICP; B2ICP_MODE_P2P_SVD = the fast pipeline
+  // false (default): neighbours from the engine's exact search on the global voxel lattice.  true: PCL-compatible
+  // map (b2icp_map_reset_octree): lattice anchored on the first point, root box grown as pcl::octree grows it,
+  // approxNearestNeighbors = PCL's greedy approxNearestSearch descent — nn_cloud as the reference builds it.
+  bool pcl_octree = false;
   int device = 0;
 };
 
@@ -293,7 +303,8 @@ class OctreeMapper {
 
   // octree_mapper.cpp:56-60.  The map lives in device memory behind the C ABI (b2icp_map_*, csrc/map.cuh).
   void resetMap() {
-    last_status = b2icp_map_reset(search_.get(), prm_.octree_resolution);
+    last_status = prm_.pcl_octree ? b2icp_map_reset_octree(search_.get(), prm_.octree_resolution)
+                                  : b2icp_map_reset(search_.get(), prm_.octree_resolution);
     map_cloud_.reset(new Cloud());
     map_cloud_stale_ = false;
   }

@@ -272,6 +272,17 @@ int b2icp_mapper_register(b2icp_handle* h, const float* xyzw, size_t n, const fl
                           b2icp_result* out);
 int b2icp_mapper_grow(b2icp_handle* h, const float* xyzw, size_t n, const float* T, size_t* n_added);
 
+/* pcl::fromROSMsg(sensor_msgs::PointCloud2, pcl::PointCloud<pcl::PointXYZ>) (icp_odometer.cpp:168,173): the x, y, z
+ * FLOAT32 fields of a PointCloud2 payload -> 16-byte {x, y, z, 1} points, in message order (row-major over height x
+ * width, row_step bytes per row, point_step bytes per point, off_* = byte offsets of the three fields inside a point).
+ * The payload is uploaded once and unpacked on the device (a strided gather); NaN / Inf coordinates are copied as
+ * they are, like fromROSMsg does (VoxelGrid / the map skip them later).  A payload whose points already are
+ * {x, y, z, pad} floats (point_step 16, offsets 0 / 4 / 8) needs no call at all: pass msg.data.data() to the cloud
+ * entry points.  out_xyzw must hold width * height points.  is_bigendian != 0 swaps the bytes of every float. */
+int b2icp_pointcloud2_to_xyzw(b2icp_handle* h, const uint8_t* data, size_t data_bytes, uint32_t width, uint32_t height,
+                              uint32_t point_step, uint32_t row_step, uint32_t off_x, uint32_t off_y, uint32_t off_z,
+                              int is_bigendian, float* out_xyzw);
+
 int b2icp_get_timing(b2icp_handle* h, b2icp_timing* out);
 /* Neighbour grid of the current target (the structure that replaces the FLANN k-d tree): cell edge,
  * dims3 = {nx, ny, nz}, mean points per occupied cell.  Any pointer may be NULL. */

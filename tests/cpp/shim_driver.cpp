@@ -7,7 +7,7 @@
 #include <cstdlib>
 #include <string>
 
-#include "../../icpslam_b200/shims/b2icp_shims.hpp"
+#include "../../icpslam_b200/shims/b2icp_ros_adapter.hpp"
 
 static b2::Cloud::Ptr load(const char* path) {
   b2::Cloud::Ptr c(new b2::Cloud());
@@ -37,12 +37,52 @@ int main(int argc, char** argv) {
     printf("{"); print_pose("a", a); printf(", "); print_pose("ab", c); printf(", "); print_pose("ident", d); printf("}\n");
     return 0;
   }
+  if (mode == "pc2") {  // fromROSMsg on a raw payload: pc2 <width> <point_step> <off_x> <off_y> <off_z> <payload file>
+    if (argc < 8) return 2;
+    try {
+      b2::IcpOdometerParams op;
+      op.mode = B2ICP_MODE_P2P_SVD;
+      b2::IcpOdometer odo(op);
+      FILE* f = fopen(argv[7], "rb");
+      if (!f) return 2;
+      std::vector<uint8_t> payload;
+      uint8_t buf[65536];
+      for (size_t k; (k = fread(buf, 1, sizeof(buf), f)) > 0;) payload.insert(payload.end(), buf, buf + k);
+      fclose(f);
+      b2::PointCloud2View v;
+      v.data = payload.data();
+      v.data_bytes = payload.size();
+      v.width = (uint32_t)atoi(argv[2]);
+      v.height = 1;
+      v.point_step = (uint32_t)atoi(argv[3]);
+      v.row_step = v.width * v.point_step;
+      v.off_x = (uint32_t)atoi(argv[4]);
+      v.off_y = (uint32_t)atoi(argv[5]);
+      v.off_z = (uint32_t)atoi(argv[6]);
+      b2::Cloud c;
+      const int rc = b2::fromROSMsg(odo.engine(), v, c);
+      printf("{\"status\": %d, \"xyzw\": [", rc);
+      for (size_t i = 0; i < c.size(); ++i)
+        printf("%s%.9g, %.9g, %.9g, %.9g", i ? ", " : "", c.points[i].x, c.points[i].y, c.points[i].z, c.points[i].w);
+      printf("]}\n");
+    } catch (const std::exception& e) {
+      fprintf(stderr, "shim_driver: %s\n", e.what());
+      return 3;
+    }
+    return 0;
+  }
   if (argc < 4) return 2;
   try {
+    // B2_SHIM_MODE=p2p selects the point-to-point pipeline; the shims' own default is the reference's GICP
+    const char* em = getenv("B2_SHIM_MODE");
+    const bool p2p = em && std::string(em) == "p2p";
     b2::IcpOdometerParams op;
     op.voxel_leaf_size = mode == "odom" ? atof(argv[2]) : 0.0;
+    if (p2p) op.mode = B2ICP_MODE_P2P_SVD;
     b2::IcpOdometer odo(op);
     b2::OctreeMapperParams mp;
+    if (p2p) mp.mode = B2ICP_MODE_P2P_SVD;
+    mp.pcl_octree = getenv("B2_SHIM_OCTREE") != nullptr;
     if (mode == "map") mp.octree_resolution = atof(argv[2]);
     std::unique_ptr<b2::OctreeMapper> mapper;
     if (mode == "map") mapper.reset(new b2::OctreeMapper(mp));
