@@ -17,7 +17,8 @@ last step and inside the timed region, hands all K*B records of every rank to ev
             results inside the timed region
   roofline  fused sweep kernel: algorithmic bytes / CUDA-event launch time, vs the measured HBM peak; nested in it:
             nn_search (the stand-alone search kernel), pairs (BASELINE configs[3]: consecutive 64k-pt sweeps, each
-            registered against its predecessor, 64 pairs per rank + the gather of the records), details
+            registered against its predecessor, 64 pairs per rank + the gather of the records), gicp (the same sweeps
+            through the reference's own estimator), details
   parity    the GPU transforms / iteration counts of the --cpu-sample sweeps against the CPU oracle's (same run)
   cpu_baseline  the CPU oracle (kind "port": the reference's PCL path cannot be built here) timed on
             this box's host cores on a bounded sample of the same workload
@@ -316,6 +317,7 @@ def main():
     ap.add_argument("--in-flight", type=int, default=8, help="streamed batches in flight (1..8)")
     ap.add_argument("--grid-cell", type=float, default=0.0, help="neighbour-grid cell edge in metres (0 = auto); tuning only")
     ap.add_argument("--no-pairs", action="store_true", help="skip the configs[3] leg")
+    ap.add_argument("--no-gicp", action="store_true", help="skip the GICP-mode leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b2icp" else args.warmup
 
@@ -491,6 +493,26 @@ def main():
     api = f"b2icp_align_batch_submit[_device] / b2icp_align_batch_wait ({args.in_flight} batches in flight)"
     e2e_value = world * Bn * args.steps / e2e_dev_s
 
+    # ---- the reference's own estimator on the same workload (GICP, icp_odometer.cpp:188 / octree_mapper.cpp:104): one
+    # b2icp_align_batch of the B sweeps of set 0 in GICP mode (scans advance in lockstep rounds), host sweeps in
+    gicp = None
+    if rank == 0 and not args.no_gicp:
+        greg = R.Registration(preset=R.PRESET_MAPPER, mode=R.MODE_GICP_BFGS, device=local_rank)
+        greg.setInputTarget(map_xyzw)
+        greg.alignBatch(h_sets[0])                     # target covariances (cached with the grid), buffers
+        best, gres = None, None
+        for _ in range(2):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            grc, gres = greg.alignBatch(h_sets[0])
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        gicp = {"workload": "the same 32 sweeps vs the 500k map, pcl::GeneralizedIterativeClosestPoint restatement (k = 20 "
+                            "covariances, Mahalanobis, BFGS), 30 outer iterations max; host sweeps in, results out",
+                "scans_per_s": Bn / best, "ms_per_scan": 1e3 * best / Bn, "rc": int(grc),
+                "mean_outer_iterations": float(np.mean([r.iterations for r in gres])),
+                "converged": int(sum(r.converged for r in gres))}
+        del greg
     pairs = None
     if not args.no_pairs:
         log("[bench] configs[3] leg")
@@ -559,6 +581,8 @@ def main():
         "frac": nn_bytes / (float(np.mean(nn_ms)) * 1e-3) / 1e9 / peak, "queries_per_s": nq / (float(np.mean(nn_ms)) * 1e-3)}
     if pairs is not None:
         roofline["pairs"] = pairs
+    if gicp is not None:
+        roofline["gicp"] = gicp
     roofline["details"] = {
         "grid_cell_m": grid["cell"], "grid_dims": list(grid["dims"]), "grid_occupancy": grid["occupancy"],
         "mean_iterations": float(its_all.mean()), "max_iterations_seen": int(its_all.max()), "api": api,

@@ -94,6 +94,7 @@ struct GridSlot {
   bool cov_valid = false;
   GridView view;
   double cell = 0, min_cell = 0;
+  double force_cell = 0;  // > 0: the cell edge is given (coarse second-pass grids of the GICP covariances), no refinement
   float mn[3], mx[3];
   double occupancy = 0;
   bool valid = false;
@@ -226,7 +227,7 @@ struct b2icp_handle {
   size_t h_gicp_partials_cap = 0;
   void* h_gicp_tasks = nullptr;  // pinned task arrays of a GICP round (gicp_host.inl)
   size_t h_gicp_tasks_cap = 0;
-  DeviceBuf gicp_tasks;
+  DeviceBuf gicp_tasks, gicp_sums, knn_tasks, knn_list2, knn_counts;
   long gicp_evals = 0, gicp_rounds = 0;
 };
 
@@ -317,9 +318,10 @@ int grids_bbox(b2icp_handle* h, GridSlot* const* g, const size_t* n, int count) 
     const bool bounded = r > 0 && std::isfinite(r) && r < 1e8;
     if (bounded) cell = std::min(cell, 0.5 * r);
     if (h->params.grid_cell > 0) cell = h->params.grid_cell;
+    if (g[i]->force_cell > 0) cell = g[i]->force_cell;
     if (!(cell > 0) || !std::isfinite(cell)) cell = 1.0;
     g[i]->cell = cell;
-    g[i]->min_cell = (h->params.grid_cell > 0) ? cell : (bounded ? std::min(cell, r / 8.0) : cell / 8.0);
+    g[i]->min_cell = (h->params.grid_cell > 0 || g[i]->force_cell > 0) ? cell : (bounded ? std::min(cell, r / 8.0) : cell / 8.0);
   }
   return B2ICP_OK;
 }
@@ -1055,7 +1057,7 @@ int b2icp_destroy(b2icp_handle* h) {
   for (DeviceBuf* b : {&h->tree_keys, &h->tree_vals, &h->map_first}) b->release();
   if (h->h_gicp_partials) cudaFreeHost(h->h_gicp_partials);
   if (h->h_gicp_tasks) cudaFreeHost(h->h_gicp_tasks);
-  h->gicp_tasks.release();
+  for (DeviceBuf* b : {&h->gicp_tasks, &h->gicp_sums, &h->knn_tasks, &h->knn_list2, &h->knn_counts}) b->release();
   if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
   return B2ICP_OK;

@@ -223,12 +223,21 @@ __device__ __forceinline__ void cov_from_keys(const float4* __restrict__ cloud, 
   for (int i = 0; i < 9; ++i) out9[i] = o[i];
 }
 
-__global__ void __launch_bounds__(128) knn_cov_kernel(GridView g, const float4* __restrict__ cloud, int n, int k,
-                                                      double eps, int max_rings, double* __restrict__ cov9,
-                                                      int* __restrict__ unresolved_list,
-                                                      unsigned int* __restrict__ unresolved_count) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+// One task = one cloud of a batch (blockIdx.y selects it): the covariances of every scan of a GICP batch are one launch.
+struct KnnTask {
+  GridView g;           // grid over the cloud
+  const float4* cloud;  // the cloud in original order
+  double* cov;          // [n][9]
+  int n;
+  int pad;
+};
+
+// k nearest neighbours + covariance of point i of task t (one thread); queued on `unresolved_list` when its k
+// neighbours do not lie within max_rings cells of its grid.
+__device__ __forceinline__ void knn_cov_point(const KnnTask& t, int task_id, int i, int k, double eps, int max_rings,
+                                              int2* __restrict__ unresolved_list, unsigned int* __restrict__ unresolved_count) {
+  const GridView& g = t.g;
+  const float4* __restrict__ cloud = t.cloud;
   const float4 q = __ldg(cloud + i);
   unsigned long long keys[kMaxK];
   for (int j = 0; j < kMaxK; ++j) keys[j] = kInfKey;
@@ -280,25 +289,85 @@ __global__ void __launch_bounds__(128) knn_cov_kernel(GridView g, const float4* 
     }
   }
   if (!resolved) {
-    unresolved_list[atomicAdd(unresolved_count, 1u)] = i;
+    unresolved_list[atomicAdd(unresolved_count, 1u)] = make_int2(task_id, i);
     return;
   }
-  cov_from_keys(cloud, keys, k, eps, cov9 + (size_t)9 * i);
+  cov_from_keys(cloud, keys, k, eps, t.cov + (size_t)9 * i);
 }
 
-// exhaustive fallback: one thread per queued point, every point of the cloud offered in sorted-array order
-__global__ void __launch_bounds__(128) knn_cov_fallback(GridView g, const float4* __restrict__ cloud, int k, double eps,
-                                                        const int* __restrict__ list,
-                                                        const unsigned int* __restrict__ count,
-                                                        double* __restrict__ cov9) {
+
+
+// every point of every cloud of the batch (blockIdx.y = cloud), on the cloud's FINE grid
+__global__ void __launch_bounds__(128) knn_cov_kernel(const KnnTask* __restrict__ tasks, int k, double eps, int max_rings,
+                                                      int2* __restrict__ unresolved_list,
+                                                      unsigned int* __restrict__ unresolved_count) {
+  const KnnTask& t = tasks[blockIdx.y];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= t.n) return;
+  knn_cov_point(t, (int)blockIdx.y, i, k, eps, max_rings, unresolved_list, unresolved_count);
+}
+
+// second pass: the points the fine grid could not settle (the sparse far field of a sweep: their 20 neighbours lie
+// metres away, dozens of fine cells) on a COARSE grid over the same cloud (cell x 4: the same ring budget reaches 4x
+// as far for the same number of rows).  The k-NN is exact on either grid, so the result does not depend on which
+// pass settled a point.
+__global__ void __launch_bounds__(128) knn_cov_list_kernel(const KnnTask* __restrict__ coarse_tasks, int k, double eps, int max_rings,
+                                                           const int2* __restrict__ list, const unsigned int* __restrict__ count,
+                                                           int2* __restrict__ unresolved_list,
+                                                           unsigned int* __restrict__ unresolved_count) {
   const unsigned int total = *count;
   for (unsigned int w = blockIdx.x * blockDim.x + threadIdx.x; w < total; w += gridDim.x * blockDim.x) {
-    const int i = list[w];
-    const float4 q = __ldg(cloud + i);
+    const int2 e = list[w];
+    knn_cov_point(coarse_tasks[e.x], e.x, e.y, k, eps, max_rings, unresolved_list, unresolved_count);
+  }
+}
+
+// Exhaustive fallback for the points whose k neighbours do not lie within `max_rings` cells (the sparse fringe of a
+// sweep): one CTA per queued point.  Every thread keeps the k best keys of its share of the cloud, then the CTA
+// extracts the k smallest of all of them in ascending order (k rounds of a block-wide minimum over the threads' list
+// heads).  Keys (d2, index) are unique, so the result is the same sorted list a sequential scan would produce.
+// (Round 1 gave every queued point to ONE thread: 65 536 sequential offers, 10.8 ms per cloud whatever the count.)
+constexpr int kKnnFbThreads = 256;
+__global__ void __launch_bounds__(kKnnFbThreads) knn_cov_fallback(const KnnTask* __restrict__ tasks, int k, double eps,
+                                                                  const int2* __restrict__ list,
+                                                                  const unsigned int* __restrict__ count) {
+  __shared__ unsigned long long s_min[kKnnFbThreads / 32];
+  __shared__ unsigned long long s_win;
+  __shared__ unsigned long long s_keys[kMaxK];
+  const unsigned int total = *count;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (unsigned int w = blockIdx.x; w < total; w += gridDim.x) {
+    const KnnTask& t = tasks[list[w].x];
+    const int i = list[w].y;
+    const float4 q = __ldg(t.cloud + i);
     unsigned long long keys[kMaxK];
     for (int j = 0; j < kMaxK; ++j) keys[j] = kInfKey;
-    knn_scan(g.pts, 0, g.n, q.x, q.y, q.z, keys, k);
-    cov_from_keys(cloud, keys, k, eps, cov9 + (size_t)9 * i);
+    for (int j = threadIdx.x; j < t.g.n; j += kKnnFbThreads) {
+      const float4 p = __ldg(t.g.pts + j);
+      knn_offer(keys, k, pack_key(sqdist3(q.x, q.y, q.z, p.x, p.y, p.z), __float_as_int(p.w)));
+    }
+    int head = 0;
+    for (int r = 0; r < k; ++r) {
+      unsigned long long mine = head < k ? keys[head] : kInfKey;
+      unsigned long long m = warp_min_key(mine);
+      if (lane == 0) s_min[warp] = m;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        unsigned long long best = s_min[0];
+        for (int x = 1; x < kKnnFbThreads / 32; ++x) best = s_min[x] < best ? s_min[x] : best;
+        s_win = best;
+        s_keys[r] = best;
+      }
+      __syncthreads();
+      if (mine == s_win && mine != kInfKey) ++head;  // keys are unique: exactly one thread owns the winner
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long out[kMaxK];
+      for (int j = 0; j < k; ++j) out[j] = s_keys[j];
+      cov_from_keys(t.cloud, out, k, eps, t.cov + (size_t)9 * i);
+    }
+    __syncthreads();
   }
 }
 
@@ -440,7 +509,15 @@ __global__ void __launch_bounds__(32) gicp_sum_kernel(const GicpFdfTask* __restr
   if (threadIdx.x >= kGicpSums) return;
   const int nblk = (t.n + kGicpThreads - 1) / kGicpThreads;
   double tot = 0.0;
-  for (int b = 0; b < nblk; ++b) tot = dadd(tot, t.partials[(size_t)b * kGicpSums + threadIdx.x]);
+  int b = 0;
+  for (; b + 8 <= nblk; b += 8) {  // the eight loads are independent of the (ordered) adds that follow
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldcg(t.partials + (size_t)(b + u) * kGicpSums + threadIdx.x);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) tot = dadd(tot, v[u]);
+  }
+  for (; b < nblk; ++b) tot = dadd(tot, __ldcg(t.partials + (size_t)b * kGicpSums + threadIdx.x));
   t.sums[threadIdx.x] = tot;
 }
 

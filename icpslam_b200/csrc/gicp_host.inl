@@ -413,21 +413,67 @@ struct GicpBFGS {
   int test_gradient(double epsabs) const { return norm(gradient) < epsabs ? kSuccess : kRunning; }
 };
 
-// K5 driver: covariances of `n` points whose grid is `g` -> cov (9 doubles per point, original order)
-int compute_covariances(b2icp_handle* h, GridSlot& g, size_t n, DeviceBuf& cov) {
+// K5 driver: covariances of `count` clouds (cloud i: grid gs[i], n[i] points) -> covs[i] (9 doubles per point, original
+// order).  Three launches for the whole batch: every point on its cloud's fine grid; the points that grid could not
+// settle on a coarse grid over the same cloud (cell x 4); what is still open, exhaustively.
+int compute_covariances_batch(b2icp_handle* h, GridSlot* const* gs, const size_t* n, DeviceBuf* const* covs, int count) {
   const int k = h->params.k_correspondences;
   if (k < 1 || k > kMaxK) return fail(h, B2ICP_ERR_INVALID_ARG, "k_correspondences must be in [1, 32]");
-  if ((size_t)k > n) return fail(h, B2ICP_ERR_TOO_FEW_POINTS, "fewer points than k_correspondences");
-  CK(cov.ensure(n * 9 * sizeof(double)));
-  CK(h->unres_list.ensure(n * sizeof(int)));
-  zero_counter<<<1, 1, 0, h->stream>>>(h->unres_count.as<unsigned int>());
-  knn_cov_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(g.view, g.pts, (int)n, k, h->params.gicp_epsilon, 6,
-                                                                     cov.as<double>(), h->unres_list.as<int>(),
-                                                                     h->unres_count.as<unsigned int>());
-  knn_cov_fallback<<<148 * 4, 128, 0, h->stream>>>(g.view, g.pts, k, h->params.gicp_epsilon, h->unres_list.as<int>(),
-                                                   h->unres_count.as<unsigned int>(), cov.as<double>());
+  if (count < 1) return B2ICP_OK;
+  if (count > kMaxBatch) return fail(h, B2ICP_ERR_INVALID_ARG, "too many clouds");
+  size_t max_n = 0, total = 0;
+  for (int i = 0; i < count; ++i) {
+    if ((size_t)k > n[i]) return fail(h, B2ICP_ERR_TOO_FEW_POINTS, "fewer points than k_correspondences");
+    CK(covs[i]->ensure(n[i] * 9 * sizeof(double)));
+    max_n = std::max(max_n, n[i]);
+    total += n[i];
+  }
+  // the coarse grids: same clouds, four times the cell edge
+  std::vector<GridSlot*> cg((size_t)count);
+  std::vector<size_t> cn(n, n + count);
+  for (int i = 0; i < count; ++i) {
+    GridSlot& c = gslot(h, (size_t)(2 * kMaxBatch + 16 + i));
+    c.pts = gs[i]->pts;
+    c.force_cell = 4.0 * gs[i]->cell;
+    cg[(size_t)i] = &c;
+  }
+  int rc = build_grids(h, cg.data(), cn.data(), count);
+  if (rc) return rc;
+  CK(h->knn_tasks.ensure((size_t)2 * count * sizeof(KnnTask)));
+  CK(h->unres_list.ensure(total * sizeof(int2)));
+  CK(h->knn_list2.ensure(total * sizeof(int2)));
+  CK(h->knn_counts.ensure(2 * sizeof(unsigned int)));
+  std::vector<KnnTask> tasks((size_t)2 * count);
+  for (int i = 0; i < count; ++i) {
+    KnnTask& f = tasks[(size_t)i];
+    f.g = gs[i]->view;
+    f.cloud = gs[i]->pts;
+    f.cov = covs[i]->as<double>();
+    f.n = (int)n[i];
+    f.pad = 0;
+    tasks[(size_t)(count + i)] = f;
+    tasks[(size_t)(count + i)].g = cg[(size_t)i]->view;
+  }
+  // (pageable source: the copy is staged by the driver before the call returns)
+  CK(cudaMemcpyAsync(h->knn_tasks.p, tasks.data(), tasks.size() * sizeof(KnnTask), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemsetAsync(h->knn_counts.p, 0, 2 * sizeof(unsigned int), h->stream));
+  const KnnTask* fine = h->knn_tasks.as<KnnTask>();
+  const KnnTask* coarse = fine + count;
+  unsigned int* c1 = h->knn_counts.as<unsigned int>();
+  unsigned int* c2 = c1 + 1;
+  knn_cov_kernel<<<dim3((unsigned)((max_n + 127) / 128), (unsigned)count, 1), 128, 0, h->stream>>>(fine, k, h->params.gicp_epsilon, 6,
+                                                                                                 h->unres_list.as<int2>(), c1);
+  knn_cov_list_kernel<<<148 * 8, 128, 0, h->stream>>>(coarse, k, h->params.gicp_epsilon, 8, h->unres_list.as<int2>(), c1,
+                                                      h->knn_list2.as<int2>(), c2);
+  knn_cov_fallback<<<148 * 4, kKnnFbThreads, 0, h->stream>>>(fine, k, h->params.gicp_epsilon, h->knn_list2.as<int2>(), c2);
   h->launches += 3;
   return B2ICP_OK;
+}
+
+int compute_covariances(b2icp_handle* h, GridSlot& g, size_t n, DeviceBuf& cov) {
+  GridSlot* gp = &g;
+  DeviceBuf* cp = &cov;
+  return compute_covariances_batch(h, &gp, &n, &cp, 1);
 }
 
 // One scan of a GICP batch: its slot, its fiber and the request it is blocked on.
@@ -603,41 +649,85 @@ int run_gicp_batch(b2icp_handle* h, int B, const float* guesses) {
     return std::chrono::duration<double, std::milli>(b - a).count();
   };
   const auto t_start = now();
-  // ---- setup per scan: work buffers and covariances (target: cached with its grid; source: own temporary grid)
+  // ---- setup: work buffers; target covariances (cached with their grids); then the grids and the covariances of all
+  // the sources of the batch, each one launch sequence for the whole batch
   size_t max_n = 0;
   int setup_rc[kMaxBatch];
-  for (int i = 0; i < B; ++i) {
-    ScanSlot& s = slot(h, (size_t)i);
-    GridSlot& g = gslot(h, s.grid);
-    const size_t n = s.src.n;
-    max_n = std::max(max_n, n);
-    setup_rc[i] = B2ICP_OK;
-    int rc = ensure_slot_work(h, s);
-    if (rc) return rc;
-    CK(s.corr_pos.ensure(n * sizeof(int)));  // sorted position of the last match: the seed of the next search
-    if (!g.cov_valid) {
-      rc = compute_covariances(h, g, (size_t)g.view.n, g.cov);
-      if (rc == B2ICP_ERR_CUDA) return rc;
-      if (rc) {  // e.g. fewer target points than k_correspondences: this scan fails, the batch goes on
-        setup_rc[i] = rc;
-        continue;
+  const int k = h->params.k_correspondences;
+  {
+    std::vector<GridSlot*> tg;
+    std::vector<size_t> tn;
+    std::vector<DeviceBuf*> tc;
+    for (int i = 0; i < B; ++i) {
+      ScanSlot& s = slot(h, (size_t)i);
+      GridSlot& g = gslot(h, s.grid);
+      const size_t n = s.src.n;
+      max_n = std::max(max_n, n);
+      setup_rc[i] = ((size_t)k > n || (size_t)k > (size_t)g.view.n) ? B2ICP_ERR_TOO_FEW_POINTS : B2ICP_OK;
+      int rc = ensure_slot_work(h, s);
+      if (rc) return rc;
+      CK(s.corr_pos.ensure(n * sizeof(int)));  // sorted position of the last match: the seed of the next search
+      const int nblk = (int)((n + kGicpThreads - 1) / kGicpThreads);
+      CK(s.mahal.ensure(n * 9 * sizeof(double)));
+      CK(s.gicp_partials.ensure((size_t)nblk * kGicpSums * sizeof(double)));
+      if (!setup_rc[i] && !g.cov_valid && std::find(tg.begin(), tg.end(), &g) == tg.end()) {
+        tg.push_back(&g);
+        tn.push_back((size_t)g.view.n);
+        tc.push_back(&g.cov);
       }
-      g.cov_valid = true;
     }
-    GridSlot& sg = gslot(h, kMaxBatch + 1);
-    sg.pts = s.src.dev();
-    GridSlot* gp = &sg;
-    size_t nn = n;
-    rc = build_grids(h, &gp, &nn, 1);
-    if (!rc) rc = compute_covariances(h, sg, n, s.cov);
-    if (rc == B2ICP_ERR_CUDA) return rc;
-    if (rc) {
-      setup_rc[i] = rc;
-      continue;
+    if (!tg.empty()) {
+      int rc = compute_covariances_batch(h, tg.data(), tn.data(), tc.data(), (int)tg.size());
+      if (rc) return rc;
+      for (GridSlot* g : tg) g->cov_valid = true;
     }
-    const int nblk = (int)((n + kGicpThreads - 1) / kGicpThreads);
-    CK(s.mahal.ensure(n * 9 * sizeof(double)));
-    CK(s.gicp_partials.ensure(((size_t)nblk + 1) * kGicpSums * sizeof(double)));  // + the scan's 14 sums
+    std::vector<GridSlot*> sg;
+    std::vector<size_t> sn;
+    std::vector<DeviceBuf*> sc;
+    for (int i = 0; i < B; ++i) {
+      if (setup_rc[i]) continue;
+      ScanSlot& s = slot(h, (size_t)i);
+      GridSlot& g = gslot(h, (size_t)(kMaxBatch + 8 + i));  // the source's own grid: only its neighbour lists are used
+      g.pts = s.src.dev();
+      sg.push_back(&g);
+      sn.push_back(s.src.n);
+      sc.push_back(&s.cov);
+    }
+    if (!sg.empty()) {
+      int rc = build_grids(h, sg.data(), sn.data(), (int)sg.size());
+      if (rc == B2ICP_ERR_NONFINITE_INPUT) {  // find the offender: build them one by one
+        rc = B2ICP_OK;
+        for (size_t q = 0, i = 0; i < (size_t)B; ++i) {
+          if (setup_rc[i]) continue;
+          GridSlot* one = sg[q];
+          size_t nn = sn[q];
+          const int r1 = build_grids(h, &one, &nn, 1);
+          if (r1 == B2ICP_ERR_CUDA) return r1;
+          if (r1) setup_rc[i] = r1;
+          ++q;
+        }
+        std::vector<GridSlot*> sg2;
+        std::vector<size_t> sn2;
+        std::vector<DeviceBuf*> sc2;
+        for (size_t q = 0, i = 0; i < (size_t)B; ++i) {
+          if (setup_rc[i] == B2ICP_ERR_TOO_FEW_POINTS) continue;
+          if (!setup_rc[i]) {
+            sg2.push_back(sg[q]);
+            sn2.push_back(sn[q]);
+            sc2.push_back(sc[q]);
+          }
+          ++q;
+        }
+        sg.swap(sg2);
+        sn.swap(sn2);
+        sc.swap(sc2);
+      }
+      if (rc) return rc;
+      if (!sg.empty()) {
+        rc = compute_covariances_batch(h, sg.data(), sn.data(), sc.data(), (int)sg.size());
+        if (rc) return rc;
+      }
+    }
   }
   if (dbg) cudaStreamSynchronize(h->stream);
   const auto t_setup = now();
@@ -658,6 +748,7 @@ int run_gicp_batch(b2icp_handle* h, int B, const float* guesses) {
     h->h_gicp_partials_cap = (size_t)kMaxBatch * kGicpSums;
   }
   CK(h->gicp_tasks.ensure((size_t)kMaxBatch * (sizeof(GicpCorrTask) + sizeof(GicpFdfTask))));
+  CK(h->gicp_sums.ensure((size_t)kMaxBatch * kGicpSums * sizeof(double)));
   GicpCorrTask* h_corr = reinterpret_cast<GicpCorrTask*>(h->h_gicp_tasks);
   GicpFdfTask* h_fdf = reinterpret_cast<GicpFdfTask*>(h_corr + kMaxBatch);
   GicpCorrTask* d_corr = h->gicp_tasks.as<GicpCorrTask>();
@@ -734,8 +825,9 @@ int run_gicp_batch(b2icp_handle* h, int B, const float* guesses) {
         t.tgt = g.pts;
         t.corr_idx = s.corr_idx.as<int>();
         t.mahal = s.mahal.as<double>();
+        (void)nblk;
         t.partials = s.gicp_partials.as<double>();
-        t.sums = s.gicp_partials.as<double>() + (size_t)nblk * kGicpSums;
+        t.sums = h->gicp_sums.as<double>() + (size_t)(nf - 1) * kGicpSums;
         t.n = n;
         t.pad = 0;
         t.a = j.eval;
@@ -754,9 +846,8 @@ int run_gicp_batch(b2icp_handle* h, int B, const float* guesses) {
       gicp_fdf_kernel<<<dim3((unsigned)((max_n + kGicpThreads - 1) / kGicpThreads), (unsigned)nf, 1), kGicpThreads, 0, h->stream>>>(d_fdf);
       gicp_sum_kernel<<<nf, 32, 0, h->stream>>>(d_fdf);
       h->launches += 2;
-      for (int k = 0; k < nf && e == cudaSuccess; ++k)
-        e = cudaMemcpyAsync(h->h_gicp_partials + (size_t)k * kGicpSums, h_fdf[k].sums, kGicpSums * sizeof(double),
-                            cudaMemcpyDeviceToHost, h->stream);
+      if (e == cudaSuccess)  // the sums of the round's scans are contiguous: one read-back
+        e = cudaMemcpyAsync(h->h_gicp_partials, h->gicp_sums.p, (size_t)nf * kGicpSums * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     if (e == cudaSuccess) e = cudaGetLastError();

@@ -62,8 +62,13 @@ int main(int argc, char** argv) {
       b2::Cloud c;
       const int rc = b2::fromROSMsg(odo.engine(), v, c);
       printf("{\"status\": %d, \"xyzw\": [", rc);
-      for (size_t i = 0; i < c.size(); ++i)
-        printf("%s%.9g, %.9g, %.9g, %.9g", i ? ", " : "", c.points[i].x, c.points[i].y, c.points[i].z, c.points[i].w);
+      auto num = [](float v) {  // JSON has no nan: Python's json reads NaN
+        if (v != v) printf("NaN"); else printf("%.9g", v);
+      };
+      for (size_t i = 0; i < c.size(); ++i) {
+        if (i) printf(", ");
+        num(c.points[i].x); printf(", "); num(c.points[i].y); printf(", "); num(c.points[i].z); printf(", "); num(c.points[i].w);
+      }
       printf("]}\n");
     } catch (const std::exception& e) {
       fprintf(stderr, "shim_driver: %s\n", e.what());
