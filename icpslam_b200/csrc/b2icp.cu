@@ -34,6 +34,7 @@
 #include "map.cuh"
 #include "nn.cuh"
 #include "nnsearch.cuh"
+#include "radix.cuh"
 #include "solve.cuh"
 
 using namespace b2;
@@ -222,6 +223,8 @@ struct b2icp_handle {
   b2icp_record* sink = nullptr;  // b2icp_set_record_sink: device records of streamed batches
   size_t sink_cap = 0, sink_used = 0;
   int w_override = 0;  // B2ICP_W: lanes per cooperative group of the stand-alone search, 8 or 32 (tuning only)
+  int nn_sort_override = -1;  // B2ICP_NN_SORT=0/1 (tuning only)
+  DeviceBuf qs_sorted, qs_cell_of, qs_rank, qs_count, qs_tiles;  // queries of the stand-alone search, sorted by target cell
   int join_d = 4;      // B2ICP_JOIN: cells of slack inside which a lane joins its group's pass (tuning only)
   double* h_gicp_partials = nullptr;  // pinned read-back of the GICP rounds: 14 sums per scan
   size_t h_gicp_partials_cap = 0;
@@ -709,12 +712,40 @@ int nn_search_impl(b2icp_handle* h, const float4* d_q, size_t n, int* d_idx, flo
   // 32 consecutive queries per cooperative group (coop.cuh); a grid that is a multiple of the SM count
   const int groups = (int)((n + 31) / 32);
   const int ctas = std::max(1, std::min((groups + kSweepThreads / 32 - 1) / (kSweepThreads / 32), 148 * kSweepMinCtas * 4));
-  if (h->w_override == 8)
-    nn_search_coop<8><<<ctas, kSweepThreads, 0, h->stream>>>(g.view, d_q, (int)n, kUnboundedRings, h->join_d, d_idx, d_d2,
-                                                             h->unres_list.as<int>(), h->unres_count.as<unsigned int>());
-  else
-    nn_search_coop<32><<<ctas, kSweepThreads, 0, h->stream>>>(g.view, d_q, (int)n, kUnboundedRings, h->join_d, d_idx, d_d2,
-                                                              h->unres_list.as<int>(), h->unres_count.as<unsigned int>());
+  const int ncell = g.view.nx * g.view.ny * g.view.nz;
+  // Large query clouds are first counting-sorted by target cell (three streaming passes over the queries and one over
+  // the cell table): groups of consecutive queries then share their candidates.  Small ones are searched in place.
+  const bool sort_queries = h->nn_sort_override >= 0 ? h->nn_sort_override != 0 : (n >= 65536 && n >= (size_t)ncell / 8);
+  const float4* q_in = d_q;
+  if (sort_queries) {
+    CK(h->qs_sorted.ensure(n * sizeof(float4)));
+    CK(h->qs_cell_of.ensure(n * sizeof(int)));
+    CK(h->qs_rank.ensure(n * sizeof(int)));
+    CK(h->qs_count.ensure((size_t)(ncell + 1 + 4) * sizeof(int)));
+    const int ntiles = (ncell + kScanTile - 1) / kScanTile;
+    CK(h->qs_tiles.ensure((size_t)ntiles * sizeof(int)));
+    CK(h->map_stats.ensure(sizeof(BBox)));
+    int* cs = h->qs_count.as<int>();
+    const int blocks = (int)((n + 255) / 256);
+    CK(cudaMemsetAsync(cs, 0, (size_t)(ncell + 1) * sizeof(int), h->stream));
+    grid_count<<<blocks, 256, 0, h->stream>>>(d_q, (int)n, g.view, h->qs_cell_of.as<int>(), h->qs_rank.as<int>(), cs);
+    scan_tile_sums<<<ntiles, kScanThreads, 0, h->stream>>>(cs, ncell, h->qs_tiles.as<int>(), h->map_stats.as<BBox>());
+    scan_of_sums<<<1, kScanThreads, 0, h->stream>>>(h->qs_tiles.as<int>(), ntiles);
+    scan_apply<<<ntiles, kScanThreads, 0, h->stream>>>(cs, ncell, h->qs_tiles.as<int>(), (int)n);
+    grid_scatter<<<blocks, 256, 0, h->stream>>>(d_q, (int)n, h->qs_cell_of.as<int>(), h->qs_rank.as<int>(), cs,
+                                                 h->qs_sorted.as<float4>());
+    h->launches += 5;
+    q_in = h->qs_sorted.as<float4>();
+  }
+#define B2_NN_LAUNCH(W, S)                                                                                                       \
+  nn_search_coop<W, S><<<ctas, kSweepThreads, 0, h->stream>>>(g.view, q_in, (int)n, kUnboundedRings, h->join_d, d_idx, d_d2,      \
+                                                              h->unres_list.as<int>(), h->unres_count.as<unsigned int>())
+  if (h->w_override == 8) {
+    if (sort_queries) B2_NN_LAUNCH(8, true); else B2_NN_LAUNCH(8, false);
+  } else {
+    if (sort_queries) B2_NN_LAUNCH(32, true); else B2_NN_LAUNCH(32, false);
+  }
+#undef B2_NN_LAUNCH
   h->launches += 2;
   return launch_brute_fallback(h, g.view, d_q, n, d_idx, d_d2);
 }
@@ -986,6 +1017,7 @@ int b2icp_create(const b2icp_params* p, b2icp_handle** out) {
   if (getenv("B2ICP_NO_GRAPH")) h->use_graphs = false;
   if (const char* e = getenv("B2ICP_W")) h->w_override = atoi(e);
   if (const char* e = getenv("B2ICP_JOIN")) h->join_d = atoi(e);
+  if (const char* e = getenv("B2ICP_NN_SORT")) h->nn_sort_override = atoi(e);
   if (const char* e = getenv("B2ICP_IN_FLIGHT")) h->max_in_flight = std::max(1, std::min(kStreamSets, atoi(e)));
   if (const char* e = getenv("B2ICP_QPT_SCHED"))
     for (const char* p = e; *p;) {
@@ -1054,7 +1086,8 @@ int b2icp_destroy(b2icp_handle* h) {
   if (h->h_bbox) cudaFreeHost(h->h_bbox);
   if (h->h_first) cudaFreeHost(h->h_first);
   if (h->h_point) cudaFreeHost(h->h_point);
-  for (DeviceBuf* b : {&h->tree_keys, &h->tree_vals, &h->map_first}) b->release();
+  for (DeviceBuf* b : {&h->tree_keys, &h->tree_vals, &h->map_first, &h->qs_sorted, &h->qs_cell_of, &h->qs_rank, &h->qs_count, &h->qs_tiles})
+    b->release();
   if (h->h_gicp_partials) cudaFreeHost(h->h_gicp_partials);
   if (h->h_gicp_tasks) cudaFreeHost(h->h_gicp_tasks);
   for (DeviceBuf* b : {&h->gicp_tasks, &h->gicp_sums, &h->knn_tasks, &h->knn_list2, &h->knn_counts}) b->release();
@@ -1484,6 +1517,62 @@ int b2icp_voxel_filter(b2icp_handle* h, const float* in_xyzw, size_t n, float le
     }
   }
   const int ncell = (int)cells;
+  // A dense per-voxel table pays while voxels are about as many as points.  A fine leaf over a wide scan (the
+  // reference's code default, 0.05 m, over a 60 m x 60 m x 10 m sweep is 2.9e8 voxels) would allocate, clear and scan
+  // gigabytes per call: such boxes take the SPARSE path — what pcl::VoxelGrid itself does — a stable radix sort of
+  // (voxel index, point index), leaders where the key changes, centroids over the runs.  Same bits as the dense path.
+  if ((size_t)ncell > 8 * n + 4096 || ncell > kMaxCells || getenv("B2ICP_VOXEL_SPARSE")) {
+    const int N = (int)n;
+    const int nchunk = (N + kSortChunk - 1) / kSortChunk, nh = kSortBins * nchunk;
+    const int stiles = (nh + kScanTile - 1) / kScanTile, ftiles = (N + kScanTile - 1) / kScanTile;
+    CK(g.cell_of.ensure((n + 8) * 4));
+    CK(g.rank.ensure((n + 8) * 4));
+    CK(g.sorted.ensure((n + 8) * 8));  // second (key, value) buffer pair
+    CK(g.cell_start.ensure(((size_t)nh + 8) * sizeof(int)));
+    CK(g.tile_sums.ensure((size_t)std::max(stiles, ftiles) * sizeof(int)));
+    CK(h->xf_out.ensure(n * sizeof(float4)));
+    CK(h->q_idx.ensure((n + 8) * sizeof(int)));
+    unsigned int* k0 = g.cell_of.as<unsigned int>();
+    unsigned int* v0 = g.rank.as<unsigned int>();
+    unsigned int* k1 = g.sorted.as<unsigned int>();
+    unsigned int* v1 = k1 + (n + 8);
+    int* hist = g.cell_start.as<int>();
+    int* flags = h->q_idx.as<int>();
+    static bool configured = false;
+    if (!configured) {
+      CK(cudaFuncSetAttribute(sort_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kSortWarps * kSortBins * sizeof(int))));
+      configured = true;
+    }
+    voxel_sparse_keys<<<blocks, 256, 0, h->stream>>>(pts, N, vp, k0, v0);
+    int bits = 1;
+    while (bits < 31 && (1ll << bits) < cells) ++bits;
+    for (int shift = 0; shift < bits; shift += kSortBits) {
+      sort_hist<<<nchunk, kSortThreads, 0, h->stream>>>(k0, N, shift, nchunk, hist);
+      scan_tile_sums<<<stiles, kScanThreads, 0, h->stream>>>(hist, nh, g.tile_sums.as<int>(), g.bbox.as<BBox>());
+      scan_of_sums<<<1, kScanThreads, 0, h->stream>>>(g.tile_sums.as<int>(), stiles);
+      scan_apply<<<stiles, kScanThreads, 0, h->stream>>>(hist, nh, g.tile_sums.as<int>(), N);
+      sort_scatter<<<nchunk, kSortThreads, kSortWarps * kSortBins * sizeof(int), h->stream>>>(k0, v0, N, shift, nchunk, hist, k1, v1);
+      h->launches += 5;
+      std::swap(k0, k1);
+      std::swap(v0, v1);
+    }
+    voxel_sparse_flags<<<blocks, 256, 0, h->stream>>>(k0, N, flags);
+    bbox_init<<<1, 32, 0, h->stream>>>(g.bbox.as<BBox>());
+    scan_tile_sums<<<ftiles, kScanThreads, 0, h->stream>>>(flags, N, g.tile_sums.as<int>(), g.bbox.as<BBox>());
+    scan_of_sums<<<1, kScanThreads, 0, h->stream>>>(g.tile_sums.as<int>(), ftiles);
+    CK(cudaMemcpyAsync(&h->h_bbox[1], g.bbox.p, sizeof(BBox), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const int n_vox = h->h_bbox[1].occupied;
+    scan_apply<<<ftiles, kScanThreads, 0, h->stream>>>(flags, N, g.tile_sums.as<int>(), n_vox);
+    voxel_sparse_centroids<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(pts, k0, v0, N, flags, h->xf_out.as<float4>());
+    h->launches += 7;
+    CK(cudaMemcpyAsync(out_xyzw, h->xf_out.p, (size_t)n_vox * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaGetLastError());
+    *n_out = (size_t)n_vox;
+    g.valid = false;
+    return B2ICP_OK;
+  }
   CK(g.cell_start.ensure(((size_t)ncell + 8) * sizeof(int)));
   CK(g.sorted.ensure(n * sizeof(float4)));
   CK(g.cell_of.ensure((n + 8) * sizeof(int)));

@@ -13,7 +13,11 @@ namespace b2 {
 // again with the radius they found (or, with nothing found, with boxes of 3 and then 10 cells either side);
 // what is still open after that (nothing within ~10 cells) goes to the exhaustive fallback of nn.cuh.
 // Algorithmic bytes per launch: 16 n_q (queries) + 16 N_t' (each target point in a touched cell once) + 8 n_q.
-template <int W>
+// SORTED: `q` is the query cloud counting-sorted by cell of the TARGET grid (grid.cuh: grid_count / scan / grid_scatter
+// with the target's GridView), q[i].w = original query index.  32 consecutive sorted queries then share one cell or a
+// few adjacent cells of a row, and the union box of a group is about one query's box: ~30 staged candidates per
+// group instead of the several hundred of 32 consecutive rays of a sweep.  Results go to the original positions.
+template <int W, bool SORTED>
 __global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) nn_search_coop(GridView g, const float4* __restrict__ q, int n,
                                                                                 int max_span, int join_d, int* __restrict__ idx,
                                                                                 float* __restrict__ d2,
@@ -64,14 +68,15 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) nn_search_coop(G
       if (!__any_sync(0xFFFFFFFFu, want)) break;
     }
     if (have) {
+      const int o = SORTED ? __float_as_int(p.w) : i;  // where the answer goes
       if (!finite) {
-        idx[i] = -1;
-        d2[i] = INFINITY;
+        idx[o] = -1;
+        d2[o] = INFINITY;
       } else if (exact) {
-        idx[i] = key_idx(top.k0);
-        d2[i] = key_d2(top.k0);
+        idx[o] = key_idx(top.k0);
+        d2[o] = key_d2(top.k0);
       } else {
-        unresolved_list[atomicAdd(unresolved_count, 1u)] = i;
+        unresolved_list[atomicAdd(unresolved_count, 1u)] = o;
       }
     }
   }

@@ -657,3 +657,24 @@ def test_pcl_compat_octree_map_mode_matches_the_oracle(R, oracle):
     icp.setInputTarget(nn_cloud)
     icp.align()
     assert np.array_equal(res.matrix(), icp.getFinalTransformation()) and res.iterations == icp.iterations
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sort", ["0", "1"])
+def test_nn_search_sorted_and_unsorted_query_paths(R, oracle, monkeypatch, sort):
+    """The stand-alone search counting-sorts large query clouds by target cell before the cooperative scan
+    (B2ICP_NN_SORT forces either path): both give the oracle's indices and distances, in the caller's order —
+    on a real sweep, with far queries (exhaustive fallback), non-finite queries and a ragged tail."""
+    monkeypatch.setenv("B2ICP_NN_SORT", sort)
+    _, _, sw = synth.sweep_sequence(3, 2)
+    rng = np.random.default_rng(9)
+    q = np.concatenate([sw[1][:40001], synth.as_xyzw(rng.uniform(300, 500, (37, 3)))])
+    q[123, 0] = np.nan
+    q[40000, 2] = np.inf
+    reg = R.Registration()
+    reg.setInputTarget(sw[0])
+    idx, d2 = reg.nearestKSearch1(q)
+    fin = np.isfinite(q[:, :3]).all(axis=1)
+    oi, od = oracle.KdTree(sw[0]).nn(q[fin])
+    assert np.array_equal(idx[fin], oi) and np.array_equal(d2[fin], od)
+    assert (idx[~fin] == -1).all()
