@@ -36,6 +36,7 @@
 #include "nnsearch.cuh"
 #include "radix.cuh"
 #include "solve.cuh"
+#include "tiny.cuh"
 
 using namespace b2;
 
@@ -95,6 +96,8 @@ struct GridSlot {
   bool cov_valid = false;
   GridView view;
   double cell = 0, min_cell = 0;
+  bool lazy = false;      // the target is set but its grid is not built yet (small targets: the single-launch path of
+                          // b2icp_align never needs one; ensure_grid() builds it for anything else)
   double force_cell = 0;  // > 0: the cell edge is given (coarse second-pass grids of the GICP covariances), no refinement
   float mn[3], mx[3];
   double occupancy = 0;
@@ -216,6 +219,9 @@ struct b2icp_handle {
   int max_in_flight = kStreamSets;  // B2ICP_IN_FLIGHT environment variable (tuning only)
   int qpt_override = 0;  // B2ICP_QPT environment variable (tuning only)
   std::vector<int> qpt_sched;  // B2ICP_QPT_SCHED="2,4,8": slab length per iteration, last value repeats (tuning only)
+  bool use_tiny = true;     // B2ICP_NO_TINY switches the single-launch path of small scan pairs off (tuning / debugging)
+  bool tiny_last = false;   // the last b2icp_align ran on it (its getFitnessScore is already in the state)
+  DeviceBuf tiny_partials;
   GraphCache graphs[kStreamSets + 1];  // one per streamed slot set, the last one for synchronous calls
   cudaStream_t capture_stream = nullptr;
   bool use_graphs = true;  // B2ICP_NO_GRAPH switches the captured loops off (tuning / debugging only)
@@ -277,6 +283,8 @@ void derive_config(b2icp_handle* h) {
   c.margin_frac = kCacheMarginFrac;
   if (const char* e = getenv("B2ICP_MARGIN")) c.margin_frac = (float)atof(e);  // tuning only
 }
+
+int ensure_grid(b2icp_handle* h, GridSlot& g);
 
 int rings_for_bound(const b2icp_handle* h, double min_cell) {
   if (!std::isfinite(h->cfg.bound2)) return kUnboundedRings;
@@ -426,11 +434,40 @@ int upload_cloud(b2icp_handle* h, Cloud& c, const float* xyzw, size_t n, bool fr
   return B2ICP_OK;
 }
 
+// The neighbour grid of a target whose build was deferred (GridSlot::lazy).
+int ensure_grid(b2icp_handle* h, GridSlot& g) {
+  if (!g.lazy) return B2ICP_OK;
+  GridSlot* gp = &g;
+  size_t n = g.tgt.n;
+  const int rc = build_grids(h, &gp, &n, 1);
+  if (!rc) g.lazy = false;
+  return rc;
+}
+
+bool tiny_target_ok(const b2icp_handle* h, size_t n) {
+  return h->use_tiny && h->params.mode == B2ICP_MODE_P2P_SVD && h->params.profile == 0 && n >= 1 && n <= (size_t)kTinyMax;
+}
+
 int set_target_impl(b2icp_handle* h, int gi, const float* xyzw, size_t n, bool from_device) {
   GridSlot& g = gslot(h, gi);
   g.valid = false;
+  g.lazy = false;
   g.tgt.valid = false;
   if (gi == 0) h->aligned = false;
+  if (gi == 0 && !from_device && xyzw && tiny_target_ok(h, n)) {
+    // a small target of the handle itself (the odometer's previous scan): the grid is built only if something other
+    // than the single-launch loop needs it.  What the build would have reported is checked here, on the host.
+    for (size_t i = 0; i < n; ++i)
+      if (!(std::isfinite(xyzw[4 * i]) && std::isfinite(xyzw[4 * i + 1]) && std::isfinite(xyzw[4 * i + 2])))
+        return fail(h, B2ICP_ERR_NONFINITE_INPUT, "target cloud holds non-finite coordinates");
+    int rc = upload_cloud(h, g.tgt, xyzw, n, false);
+    if (rc) return rc;
+    g.pts = g.tgt.raw.as<float4>();
+    g.cov_valid = false;
+    g.lazy = true;
+    g.valid = true;
+    return B2ICP_OK;
+  }
   int rc = upload_cloud(h, g.tgt, xyzw, n, from_device);
   if (rc) return rc;
   g.pts = g.tgt.raw.as<float4>();
@@ -480,7 +517,9 @@ int run_batch(b2icp_handle* h, int B, const float* guesses, int slot0 = 0, bool 
   for (int i = 0; i < B; ++i) {
     ScanSlot& s = slot(h, (size_t)(slot0 + i));
     GridSlot& g = gslot(h, s.grid);
-    int rc = ensure_slot_work(h, s);
+    int rc = ensure_grid(h, g);
+    if (rc) return rc;
+    rc = ensure_slot_work(h, s);
     if (rc) return rc;
     max_n = std::max(max_n, s.src.n);
     min_cell = std::min(min_cell, (double)g.view.cell);
@@ -668,6 +707,13 @@ int launch_brute_fallback(b2icp_handle* h, const GridView& view, const float4* d
 int enqueue_fitness(b2icp_handle* h, int i, double max_range) {
   ScanSlot& s = slot(h, i);
   GridSlot& g = gslot(h, s.grid);
+  if (g.lazy) {  // the loop ran without a grid (single-launch path): build it and point the scan's task at it
+    int rc = ensure_grid(h, g);
+    if (rc) return rc;
+    h->h_tasks[i].grid = g.view;
+    h->h_tasks[i].pad = 0;
+    CK(cudaMemcpyAsync(h->tasks.as<ScanTask>() + i, h->h_tasks + i, sizeof(ScanTask), cudaMemcpyHostToDevice, h->stream));
+  }
   const size_t n = s.src.n;
   CK(h->query.ensure(n * sizeof(float4)));
   CK(h->q_idx.ensure(n * sizeof(int)));
@@ -707,6 +753,10 @@ int launch_brute_fallback(b2icp_handle* h, const GridView& view, const float4* d
 
 int nn_search_impl(b2icp_handle* h, const float4* d_q, size_t n, int* d_idx, float* d_d2, int grid_index = 0) {
   GridSlot& g = gslot(h, (size_t)grid_index);
+  {
+    int rc = ensure_grid(h, g);
+    if (rc) return rc;
+  }
   CK(h->unres_list.ensure(n * sizeof(int)));
   zero_counter<<<1, 1, 0, h->stream>>>(h->unres_count.as<unsigned int>());
   // 32 consecutive queries per cooperative group (coop.cuh); a grid that is a multiple of the SM count
@@ -1015,6 +1065,7 @@ int b2icp_create(const b2icp_params* p, b2icp_handle** out) {
   derive_config(h);
   if (const char* e = getenv("B2ICP_QPT")) h->qpt_override = atoi(e);
   if (getenv("B2ICP_NO_GRAPH")) h->use_graphs = false;
+  if (getenv("B2ICP_NO_TINY")) h->use_tiny = false;
   if (const char* e = getenv("B2ICP_W")) h->w_override = atoi(e);
   if (const char* e = getenv("B2ICP_JOIN")) h->join_d = atoi(e);
   if (const char* e = getenv("B2ICP_NN_SORT")) h->nn_sort_override = atoi(e);
@@ -1036,6 +1087,7 @@ int b2icp_create(const b2icp_params* p, b2icp_handle** out) {
   slot(h, 0);
   gslot(h, 0);
   bool ok = cudaSetDevice(h->device) == cudaSuccess &&
+            cudaFuncSetAttribute(icp_tiny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTinyMax * 16) == cudaSuccess &&
             cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaMallocHost((void**)&h->h_states, sizeof(IcpState) * kSlots) == cudaSuccess &&
             cudaMallocHost((void**)&h->h_tasks, sizeof(ScanTask) * kSlots) == cudaSuccess &&
@@ -1090,6 +1142,7 @@ int b2icp_destroy(b2icp_handle* h) {
     b->release();
   if (h->h_gicp_partials) cudaFreeHost(h->h_gicp_partials);
   if (h->h_gicp_tasks) cudaFreeHost(h->h_gicp_tasks);
+  h->tiny_partials.release();
   for (DeviceBuf* b : {&h->gicp_tasks, &h->gicp_sums, &h->knn_tasks, &h->knn_list2, &h->knn_counts}) b->release();
   if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -1154,6 +1207,8 @@ int b2icp_promote_source_to_target(b2icp_handle* h) {
   ScanSlot& s = slot(h, 0);
   GridSlot& g = gslot(h, 0);
   if (!s.src.valid || s.src.ext) return fail(h, B2ICP_ERR_NO_SOURCE, "no source cloud set");
+  // a small source that has just been registered successfully is known to be finite: its grid can wait
+  const bool defer = h->aligned && h->h_states[0].status == 0 && tiny_target_ok(h, s.src.n);
   std::swap(s.src.raw, g.tgt.raw);
   g.tgt.n = s.src.n;
   g.tgt.valid = true;
@@ -1161,11 +1216,71 @@ int b2icp_promote_source_to_target(b2icp_handle* h) {
   s.src.valid = false;
   s.src.n = 0;
   h->aligned = false;
+  if (defer) {
+    g.cov_valid = false;
+    g.lazy = true;
+    g.valid = true;
+    return B2ICP_OK;
+  }
+  g.lazy = false;
   GridSlot* gp = &g;
   size_t n = g.tgt.n;
   int rc = build_grids(h, &gp, &n, 1);
   if (rc) g.tgt.valid = false;
   return rc;
+}
+
+// The whole loop of one small scan pair in one cooperative launch (tiny.cuh); the caller reads the state back.
+static int run_tiny(b2icp_handle* h, const float* guess) {
+  ScanSlot& s = slot(h, 0);
+  GridSlot& g = gslot(h, 0);
+  const int ns = (int)s.src.n, nt = (int)g.tgt.n;
+  const int G = (ns + kTinyQpc - 1) / kTinyQpc;
+  int rc = ensure_slot_work(h, s);
+  if (rc) return rc;
+  CK(h->tiny_partials.ensure((size_t)2 * G * kNumSums * sizeof(double)));
+  IcpState& st = h->h_states[0];
+  std::memset(&st, 0, sizeof(st));
+  for (int k = 0; k < 16; ++k) {
+    const float v = guess ? guess[k] : ((k % 5 == 0) ? 1.f : 0.f);
+    st.Tinc[k] = v;
+    st.final_T[k] = v;
+  }
+  st.mse = std::nan("");
+  st.prev_mse = DBL_MAX;
+  ScanTask& t = h->h_tasks[0];  // what getFitnessScore / the aligned cloud read afterwards
+  t.grid = g.view;
+  t.src = s.src.dev();
+  t.cur = s.cur.as<float4>();
+  t.corr_idx = s.corr_idx.as<int>();
+  t.corr_d2 = s.corr_d2.as<float>();
+  t.c0 = s.c0.as<float4>();
+  t.c1 = s.c1.as<float4>();
+  t.c2 = s.c2.as<float4>();
+  t.partials = s.partials.as<double>();
+  t.state = h->states.as<IcpState>();
+  t.n = ns;
+  t.pad = 0;
+  CK(cudaMemcpyAsync(h->tasks.p, h->h_tasks, sizeof(ScanTask), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(h->states.p, h->h_states, sizeof(IcpState), cudaMemcpyHostToDevice, h->stream));
+  TinyArgs a;
+  a.src = s.src.dev();
+  a.tgt = g.pts;
+  a.cur = s.cur.as<float4>();
+  a.corr_idx = s.corr_idx.as<int>();
+  a.corr_d2 = s.corr_d2.as<float>();
+  a.partials = h->tiny_partials.as<double>();
+  a.state = h->states.as<IcpState>();
+  a.cfg = h->cfg;
+  a.ns = ns;
+  a.nt = nt;
+  a.with_fitness = 1;
+  void* args[] = {&a};
+  CK(cudaLaunchCooperativeKernel((const void*)icp_tiny_kernel, dim3((unsigned)G), dim3(kTinyThreads), args, (size_t)nt * sizeof(float4),
+                                 h->stream));
+  h->launches += 1;
+  h->last_batch = 1;
+  return B2ICP_OK;
 }
 
 int b2icp_align(b2icp_handle* h, const float* guess, b2icp_result* out, float* aligned_xyzw) {
@@ -1180,8 +1295,13 @@ int b2icp_align(b2icp_handle* h, const float* guess, b2icp_result* out, float* a
   if (!gslot(h, 0).valid) return fail(h, B2ICP_ERR_NO_TARGET, "no target cloud set");
   h->aligned = false;
   const bool gicp = h->params.mode == B2ICP_MODE_GICP_BFGS;
-  int rc = gicp ? run_gicp(h, guess) : run_batch(h, 1, guess);
+  // small pairs (the odometer's 1080-point scans): the whole loop and getFitnessScore in one launch, no grid
+  const bool tiny = !gicp && !s.src.ext && tiny_target_ok(h, s.src.n) && tiny_target_ok(h, gslot(h, 0).tgt.n) &&
+                    gslot(h, 0).pts == gslot(h, 0).tgt.raw.as<float4>();
+  h->tiny_last = false;
+  int rc = gicp ? run_gicp(h, guess) : (tiny ? run_tiny(h, guess) : run_batch(h, 1, guess));
   if (rc) return rc;
+  h->tiny_last = tiny;
   const size_t n = s.src.n;
   if (aligned_xyzw) {
     CK(h->xf_out.ensure(n * sizeof(float4)));
@@ -1211,6 +1331,10 @@ int b2icp_fitness(b2icp_handle* h, double max_range, double* out) {
   std::lock_guard<std::mutex> lk(h->mu);
   CK(cudaSetDevice(h->device));
   if (!h->aligned) return fail(h, B2ICP_ERR_NOT_ALIGNED, "b2icp_fitness needs a completed b2icp_align");
+  if (h->tiny_last && !(max_range < DBL_MAX) && h->h_states[0].status == 0) {  // computed by the single-launch loop
+    *out = fitness_value(h->h_states[0]);
+    return B2ICP_OK;
+  }
   int rc = enqueue_fitness(h, 0, max_range);
   if (rc) return rc;
   CK(cudaMemcpyAsync(h->h_states, h->states.p, sizeof(IcpState), cudaMemcpyDeviceToHost, h->stream));
@@ -2083,6 +2207,11 @@ int b2icp_get_grid_info(b2icp_handle* h, float* cell, int32_t* dims3, double* oc
   std::lock_guard<std::mutex> lk(h->mu);
   GridSlot& g = gslot(h, 0);
   if (!g.valid) return fail(h, B2ICP_ERR_NO_TARGET, "no target cloud set");
+  {
+    CK(cudaSetDevice(h->device));
+    int rc = ensure_grid(h, g);
+    if (rc) return rc;
+  }
   if (cell) *cell = g.view.cell;
   if (dims3) {
     dims3[0] = g.view.nx;

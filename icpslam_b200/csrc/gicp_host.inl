@@ -661,6 +661,10 @@ int run_gicp_batch(b2icp_handle* h, int B, const float* guesses) {
     for (int i = 0; i < B; ++i) {
       ScanSlot& s = slot(h, (size_t)i);
       GridSlot& g = gslot(h, s.grid);
+      {
+        int rc = ensure_grid(h, g);
+        if (rc) return rc;
+      }
       const size_t n = s.src.n;
       max_n = std::max(max_n, n);
       setup_rc[i] = ((size_t)k > n || (size_t)k > (size_t)g.view.n) ? B2ICP_ERR_TOO_FEW_POINTS : B2ICP_OK;
