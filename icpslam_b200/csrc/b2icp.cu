@@ -52,6 +52,7 @@ constexpr float kCacheMarginFrac = 0.05f;  // nncache.cuh: box-search margin as 
 constexpr int kStreamedQpt = 32;          // slab length of streamed batches (4: 15.5k, 8: 18.6k, 16: 21.7k, 32: 23.2k scans/s)
 constexpr int kFirstSweepQpt = 2;         // slab length (x 32 queries per warp) of the first sweep of a batch
 constexpr int kMaxBatch = 64;             // scans advanced together by one sweep launch
+constexpr int kGicpGroups = 4;            // groups a GICP batch can be dealt to (device rounds overlapping host updates)
 constexpr int kStreamSets = 8;            // streamed batches in flight (b2icp_align_batch_submit / _wait)
 constexpr int kSetSlots = 32;             // scans per streamed batch
 constexpr int kSlots = kStreamSets * kSetSlots > kMaxBatch ? kStreamSets * kSetSlots : kMaxBatch;  // state / task records
@@ -238,6 +239,8 @@ struct b2icp_handle {
   size_t h_gicp_tasks_cap = 0;
   DeviceBuf gicp_tasks, gicp_sums, knn_tasks, knn_list2, knn_counts;
   long gicp_evals = 0, gicp_rounds = 0;
+  int gicp_groups = 2;  // B2ICP_GICP_GROUPS (tuning only)
+  cudaStream_t gicp_streams[kGicpGroups] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -282,6 +285,22 @@ void derive_config(b2icp_handle* h) {
   c.max_rings = 1;
   c.margin_frac = kCacheMarginFrac;
   if (const char* e = getenv("B2ICP_MARGIN")) c.margin_frac = (float)atof(e);  // tuning only
+}
+
+// The fused sweep, one instantiation per slab length.
+template <int QPT>
+void launch_sweep_one(dim3 grid, cudaStream_t st, const ScanTask* tasks, const IcpConfig& cfg) {
+  icp_sweep_p2p<QPT><<<grid, kSweepThreads, 0, st>>>(tasks, cfg);
+}
+void launch_sweep(int q, dim3 grid, cudaStream_t st, const ScanTask* tasks, const IcpConfig& cfg) {
+  switch (q) {
+    case 32: launch_sweep_one<32>(grid, st, tasks, cfg); break;
+    case 16: launch_sweep_one<16>(grid, st, tasks, cfg); break;
+    case 8: launch_sweep_one<8>(grid, st, tasks, cfg); break;
+    case 4: launch_sweep_one<4>(grid, st, tasks, cfg); break;
+    case 2: launch_sweep_one<2>(grid, st, tasks, cfg); break;
+    default: launch_sweep_one<1>(grid, st, tasks, cfg); break;
+  }
 }
 
 int ensure_grid(b2icp_handle* h, GridSlot& g);
@@ -588,18 +607,7 @@ int run_batch(b2icp_handle* h, int B, const float* guesses, int slot0 = 0, bool 
       if (with_events) cudaEventRecord(h->events[2 + 2 * it], st);
       const int q = qpt_at(it);
       const dim3 grid((unsigned)((max_n + (size_t)kSweepThreads * q - 1) / ((size_t)kSweepThreads * q)), (unsigned)B, 1);
-      if (q == 32)
-        icp_sweep_p2p<32><<<grid, kSweepThreads, 0, st>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
-      else if (q == 16)
-        icp_sweep_p2p<16><<<grid, kSweepThreads, 0, st>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
-      else if (q == 8)
-        icp_sweep_p2p<8><<<grid, kSweepThreads, 0, st>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
-      else if (q == 4)
-        icp_sweep_p2p<4><<<grid, kSweepThreads, 0, st>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
-      else if (q == 2)
-        icp_sweep_p2p<2><<<grid, kSweepThreads, 0, st>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
-      else
-        icp_sweep_p2p<1><<<grid, kSweepThreads, 0, st>>>(h->tasks.as<ScanTask>() + slot0, h->cfg);
+      launch_sweep(q, grid, st, h->tasks.as<ScanTask>() + slot0, h->cfg);
       if (with_events) cudaEventRecord(h->events[3 + 2 * it], st);
     }
     // correspondences of the last sweep, for b2icp_get_correspondences
@@ -1065,6 +1073,7 @@ int b2icp_create(const b2icp_params* p, b2icp_handle** out) {
   derive_config(h);
   if (const char* e = getenv("B2ICP_QPT")) h->qpt_override = atoi(e);
   if (getenv("B2ICP_NO_GRAPH")) h->use_graphs = false;
+  if (const char* e = getenv("B2ICP_GICP_GROUPS")) h->gicp_groups = std::max(1, atoi(e));
   if (getenv("B2ICP_NO_TINY")) h->use_tiny = false;
   if (const char* e = getenv("B2ICP_W")) h->w_override = atoi(e);
   if (const char* e = getenv("B2ICP_JOIN")) h->join_d = atoi(e);
@@ -1133,6 +1142,8 @@ int b2icp_destroy(b2icp_handle* h) {
   for (GraphCache& gc : h->graphs)
     if (gc.exec) cudaGraphExecDestroy(gc.exec);
   if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
+  for (int k = 0; k < kGicpGroups; ++k)
+    if (h->gicp_streams[k]) cudaStreamDestroy(h->gicp_streams[k]);
   if (h->h_states) cudaFreeHost(h->h_states);
   if (h->h_tasks) cudaFreeHost(h->h_tasks);
   if (h->h_bbox) cudaFreeHost(h->h_bbox);

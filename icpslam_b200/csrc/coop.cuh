@@ -26,39 +26,11 @@
 #include "common.cuh"
 #include "grid.cuh"
 #include "nncache.cuh"
+#include "tma.cuh"
 
 namespace b2 {
 
 constexpr int kCoopCap = 256;  // staged candidates per warp and chunk (4 KB of shared memory)
-
-__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned int bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "B2_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra B2_DONE;\n"
-      "bra B2_WAIT;\n"
-      "B2_DONE:\n"
-      "}" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-// 1-D bulk-async copy global -> shared::cta, `bytes` a multiple of 16, both addresses 16-byte aligned
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned int bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
 
 // Per-lane state of a cooperative scan: the two nearest candidates and the third distance.
 struct CoopTop {

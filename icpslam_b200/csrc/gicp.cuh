@@ -302,8 +302,11 @@ __global__ void __launch_bounds__(128) knn_cov_kernel(const KnnTask* __restrict_
                                                       int2* __restrict__ unresolved_list,
                                                       unsigned int* __restrict__ unresolved_count) {
   const KnnTask& t = tasks[blockIdx.y];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= t.n) return;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= t.n) return;
+  // threads take the points in CELL order (the grid is over the same cloud): the lanes of a warp walk the same
+  // cells, their loads coalesce and their trip counts agree; the result lands at the point's original index
+  const int i = __float_as_int(__ldg(t.g.pts + j).w);
   knn_cov_point(t, (int)blockIdx.y, i, k, eps, max_rings, unresolved_list, unresolved_count);
 }
 
@@ -430,7 +433,7 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) gicp_corr_kernel
   for (int e = 0; e < 9; ++e) temp[e] = dadd(temp[e], C2[e]);
   mat3_inv(temp, M);
 #pragma unroll
-  for (int e = 0; e < 9; ++e) t.mahal[(size_t)9 * i + e] = M[e];
+  for (int e = 0; e < 9; ++e) t.mahal[(size_t)e * t.n + i] = M[e];  // nine planes of n: the cost functor reads them coalesced
 }
 
 // ---- G3: one evaluation of the cost functor (OptimizationFunctorWithIndices::fdf) ---------------------
@@ -444,16 +447,24 @@ struct GicpFdfTask {
   const float4* tgt;
   const int* corr_idx;
   const double* mahal;
-  double* partials;  // [ceil(n / 256)][kGicpSums]
-  double* sums;      // [kGicpSums]: the CTA sums added in order (gicp_sum_kernel)
+  double* partials;      // [ceil(n / 256)][kGicpSums]
+  double* sums;          // [kGicpSums]: the CTA sums added in CTA order; may point into mapped pinned host memory
+  unsigned int* ticket;  // CTAs of this scan that have stored their partials (zero between launches)
   int n;
   int pad;
   GicpEvalArgs a;
 };
 
-__global__ void __launch_bounds__(kGicpThreads) gicp_fdf_kernel(const GicpFdfTask* __restrict__ tasks) {
+// The tasks of one launch travel as a kernel parameter (no task upload in front of every evaluation).
+constexpr int kGicpParamTasks = 16;
+struct GicpFdfBatch {
+  GicpFdfTask t[kGicpParamTasks];
+};
+
+__global__ void __launch_bounds__(kGicpThreads) gicp_fdf_kernel(const __grid_constant__ GicpFdfBatch batch) {
   __shared__ double smem[kGicpThreads / 32][kGicpSums];
-  const GicpFdfTask& t = tasks[blockIdx.y];
+  __shared__ bool s_last;
+  const GicpFdfTask& t = batch.t[blockIdx.y];
   const GicpEvalArgs& a = t.a;
   const int n = t.n;
   if (blockIdx.x * kGicpThreads >= n) return;
@@ -467,7 +478,9 @@ __global__ void __launch_bounds__(kGicpThreads) gicp_fdf_kernel(const GicpFdfTas
     const float4 pt = __ldg(t.tgt + ti);
     const float4 pp = xform_f(a.Tx, ps.x, ps.y, ps.z);
     const double r0 = (double)fsub(pp.x, pt.x), r1 = (double)fsub(pp.y, pt.y), r2 = (double)fsub(pp.z, pt.z);
-    const double* M = t.mahal + (size_t)9 * i;
+    double M[9];  // plane e of the scan's Mahalanobis matrices at [e * n + i]
+#pragma unroll
+    for (int e = 0; e < 9; ++e) M[e] = __ldg(t.mahal + (size_t)e * n + i);
     const double t0 = dadd(dadd(dmul(M[0], r0), dmul(M[1], r1)), dmul(M[2], r2));
     const double t1 = dadd(dadd(dmul(M[3], r0), dmul(M[4], r1)), dmul(M[5], r2));
     const double t2 = dadd(dadd(dmul(M[6], r0), dmul(M[7], r1)), dmul(M[8], r2));
@@ -482,16 +495,58 @@ __global__ void __launch_bounds__(kGicpThreads) gicp_fdf_kernel(const GicpFdfTas
     v[10] = dmul(b2, t0); v[11] = dmul(b2, t1); v[12] = dmul(b2, t2);
     v[13] = 1.0;
   }
-  // the fixed tree: xor butterfly inside the warp, warp sums in order, CTA sums in order (gicp_sum_kernel)
-#pragma unroll
-  for (int c = 0; c < kGicpSums; ++c) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v[c] = dadd(v[c], __shfl_xor_sync(0xFFFFFFFFu, v[c], o));
-  }
+  // the fixed tree: xor butterfly 16, 8, 4, 2, 1 inside the warp, warp sums in order, CTA sums in order (last
+  // CTA, below).  The butterfly runs as a reduce-scatter: at distance o a lane keeps half of its columns and
+  // hands the other half to its partner, so column c ends up complete in one lane after 16 + 8 + 4 + 2 + 1
+  // exchanges instead of 14 x 5.  Every sum is the same pair of operands as in the plain butterfly (IEEE addition
+  // commutes), so the value of each column is bit-identical to it.
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) {
+  double w16[16];
 #pragma unroll
-    for (int c = 0; c < kGicpSums; ++c) smem[warp][c] = v[c];
+  for (int c = 0; c < 16; ++c) w16[c] = c < kGicpSums ? v[c] : 0.0;
+  // distance 16: lanes with bit 4 clear keep columns 0..7, the others 8..15
+  double w8[8];
+  {
+    const bool up = (lane & 16) != 0;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const double give = up ? w16[c] : w16[8 + c];
+      const double keep = up ? w16[8 + c] : w16[c];
+      w8[c] = dadd(keep, __shfl_xor_sync(0xFFFFFFFFu, give, 16));
+    }
+  }
+  double w4[4];
+  {
+    const bool up = (lane & 8) != 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const double give = up ? w8[c] : w8[4 + c];
+      const double keep = up ? w8[4 + c] : w8[c];
+      w4[c] = dadd(keep, __shfl_xor_sync(0xFFFFFFFFu, give, 8));
+    }
+  }
+  double w2[2];
+  {
+    const bool up = (lane & 4) != 0;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const double give = up ? w4[c] : w4[2 + c];
+      const double keep = up ? w4[2 + c] : w4[c];
+      w2[c] = dadd(keep, __shfl_xor_sync(0xFFFFFFFFu, give, 4));
+    }
+  }
+  double w1;
+  {
+    const bool up = (lane & 2) != 0;
+    const double give = up ? w2[0] : w2[1];
+    const double keep = up ? w2[1] : w2[0];
+    w1 = dadd(keep, __shfl_xor_sync(0xFFFFFFFFu, give, 2));
+  }
+  w1 = dadd(w1, __shfl_xor_sync(0xFFFFFFFFu, w1, 1));
+  // lane l now holds column 8 * bit4 + 4 * bit3 + 2 * bit2 + bit1 of the warp
+  {
+    const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+    if ((lane & 1) == 0 && col < kGicpSums) smem[warp][col] = w1;
   }
   __syncthreads();
   if (threadIdx.x < kGicpSums) {
@@ -499,26 +554,33 @@ __global__ void __launch_bounds__(kGicpThreads) gicp_fdf_kernel(const GicpFdfTas
 #pragma unroll
     for (int w = 0; w < kGicpThreads / 32; ++w) s = dadd(s, smem[w][threadIdx.x]);
     t.partials[(size_t)blockIdx.x * kGicpSums + threadIdx.x] = s;
+    __threadfence();
   }
-}
-
-// The last level of the tree: the CTA sums of a scan added in CTA order (what the host loop of round 1 did after a
-// read-back of every partial; now 14 doubles per scan come back instead of 14 per CTA).
-__global__ void __launch_bounds__(32) gicp_sum_kernel(const GicpFdfTask* __restrict__ tasks) {
-  const GicpFdfTask& t = tasks[blockIdx.x];
-  if (threadIdx.x >= kGicpSums) return;
-  const int nblk = (t.n + kGicpThreads - 1) / kGicpThreads;
+  __syncthreads();
+  // The last level of the tree, by whichever CTA of the scan finishes last: the CTA sums added in CTA order
+  // (a launch-independent order), 14 doubles per scan written where the host reads them.
+  const int nblk = (n + kGicpThreads - 1) / kGicpThreads;
+  if (threadIdx.x == 0) s_last = atomicAdd(t.ticket, 1u) == (unsigned int)(nblk - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // all threads fetch the CTA sums (kGicpThreads CTAs per trip, coalesced, every load in flight at once); then
+  // thread c adds column c in CTA order out of shared memory: the order of the adds is the definition's, only
+  // the loads are no longer one dependent round trip per eight CTAs
+  __shared__ double s_part[kGicpThreads][kGicpSums];
   double tot = 0.0;
-  int b = 0;
-  for (; b + 8 <= nblk; b += 8) {  // the eight loads are independent of the (ordered) adds that follow
-    double v[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = __ldcg(t.partials + (size_t)(b + u) * kGicpSums + threadIdx.x);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) tot = dadd(tot, v[u]);
+  for (int b0 = 0; b0 < nblk; b0 += kGicpThreads) {
+    const int cnt = min(kGicpThreads, nblk - b0);
+    const double* src = t.partials + (size_t)b0 * kGicpSums;
+    double* dst = &s_part[0][0];
+    for (int w = threadIdx.x; w < cnt * kGicpSums; w += kGicpThreads) dst[w] = __ldcg(src + w);
+    __syncthreads();
+    if (threadIdx.x < kGicpSums)
+      for (int b = 0; b < cnt; ++b) tot = dadd(tot, s_part[b][threadIdx.x]);
+    __syncthreads();
   }
-  for (; b < nblk; ++b) tot = dadd(tot, __ldcg(t.partials + (size_t)b * kGicpSums + threadIdx.x));
-  t.sums[threadIdx.x] = tot;
+  if (threadIdx.x < kGicpSums) t.sums[threadIdx.x] = tot;
+  if (threadIdx.x == 0) *t.ticket = 0;
 }
 
 }  // namespace b2

@@ -437,8 +437,15 @@ int compute_covariances_batch(b2icp_handle* h, GridSlot* const* gs, const size_t
     c.force_cell = 4.0 * gs[i]->cell;
     cg[(size_t)i] = &c;
   }
+  const bool dbg = getenv("B2ICP_GICP_DEBUG") != nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
   int rc = build_grids(h, cg.data(), cn.data(), count);
   if (rc) return rc;
+  if (dbg) {
+    cudaStreamSynchronize(h->stream);
+    fprintf(stderr, "[b2icp]   covariances of %d cloud(s): coarse grids %.2f ms\n", count,
+            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  }
   CK(h->knn_tasks.ensure((size_t)2 * count * sizeof(KnnTask)));
   CK(h->unres_list.ensure(total * sizeof(int2)));
   CK(h->knn_list2.ensure(total * sizeof(int2)));
@@ -697,8 +704,17 @@ int run_gicp_batch(b2icp_handle* h, int B, const float* guesses) {
       sn.push_back(s.src.n);
       sc.push_back(&s.cov);
     }
+    if (dbg) {
+      cudaStreamSynchronize(h->stream);
+      fprintf(stderr, "[b2icp]   setup: slots + target covariances %.2f ms\n", ms(t_start, now()));
+    }
+    const auto t_sg = now();
     if (!sg.empty()) {
       int rc = build_grids(h, sg.data(), sn.data(), (int)sg.size());
+      if (dbg) {
+        cudaStreamSynchronize(h->stream);
+        fprintf(stderr, "[b2icp]   setup: %d source grids %.2f ms\n", (int)sg.size(), ms(t_sg, now()));
+      }
       if (rc == B2ICP_ERR_NONFINITE_INPUT) {  // find the offender: build them one by one
         rc = B2ICP_OK;
         for (size_t q = 0, i = 0; i < (size_t)B; ++i) {
@@ -735,28 +751,30 @@ int run_gicp_batch(b2icp_handle* h, int B, const float* guesses) {
   }
   if (dbg) cudaStreamSynchronize(h->stream);
   const auto t_setup = now();
-  // ---- round buffers: task arrays (pinned + device) and the sums that come back
-  const size_t task_bytes = (size_t)B * (sizeof(GicpCorrTask) + sizeof(GicpFdfTask));
+  // ---- round buffers: task arrays (pinned + device) and the sums that come back, one region per group
+  constexpr size_t kTaskSlots = (size_t)kGicpGroups * kMaxBatch;
+  const size_t task_bytes = kTaskSlots * sizeof(GicpCorrTask);
   if (h->h_gicp_tasks_cap < task_bytes) {
     if (h->h_gicp_tasks) cudaFreeHost(h->h_gicp_tasks);
     h->h_gicp_tasks = nullptr;
     h->h_gicp_tasks_cap = 0;
-    CK(cudaMallocHost((void**)&h->h_gicp_tasks, (size_t)kMaxBatch * (sizeof(GicpCorrTask) + sizeof(GicpFdfTask))));
-    h->h_gicp_tasks_cap = (size_t)kMaxBatch * (sizeof(GicpCorrTask) + sizeof(GicpFdfTask));
+    CK(cudaMallocHost((void**)&h->h_gicp_tasks, task_bytes));
+    h->h_gicp_tasks_cap = task_bytes;
   }
-  if (h->h_gicp_partials_cap < (size_t)kMaxBatch * kGicpSums) {
+  if (h->h_gicp_partials_cap < kTaskSlots * kGicpSums) {
     if (h->h_gicp_partials) cudaFreeHost(h->h_gicp_partials);
     h->h_gicp_partials = nullptr;
     h->h_gicp_partials_cap = 0;
-    CK(cudaMallocHost((void**)&h->h_gicp_partials, (size_t)kMaxBatch * kGicpSums * sizeof(double)));
-    h->h_gicp_partials_cap = (size_t)kMaxBatch * kGicpSums;
+    CK(cudaMallocHost((void**)&h->h_gicp_partials, kTaskSlots * kGicpSums * sizeof(double)));
+    h->h_gicp_partials_cap = kTaskSlots * kGicpSums;
   }
-  CK(h->gicp_tasks.ensure((size_t)kMaxBatch * (sizeof(GicpCorrTask) + sizeof(GicpFdfTask))));
-  CK(h->gicp_sums.ensure((size_t)kMaxBatch * kGicpSums * sizeof(double)));
+  CK(h->gicp_tasks.ensure(task_bytes));
+  if (!h->gicp_sums.p) {  // per-scan tickets of the cost-functor kernel's last-CTA sum: zero between launches
+    CK(h->gicp_sums.ensure((size_t)kMaxBatch * sizeof(unsigned int)));
+    CK(cudaMemsetAsync(h->gicp_sums.p, 0, (size_t)kMaxBatch * sizeof(unsigned int), h->stream));
+  }
   GicpCorrTask* h_corr = reinterpret_cast<GicpCorrTask*>(h->h_gicp_tasks);
-  GicpFdfTask* h_fdf = reinterpret_cast<GicpFdfTask*>(h_corr + kMaxBatch);
   GicpCorrTask* d_corr = h->gicp_tasks.as<GicpCorrTask>();
-  GicpFdfTask* d_fdf = reinterpret_cast<GicpFdfTask*>(d_corr + kMaxBatch);
 
   // ---- one fiber per scan
   std::vector<std::unique_ptr<GicpJob>> jobs;
@@ -784,31 +802,66 @@ int run_gicp_batch(b2icp_handle* h, int B, const float* guesses) {
     j.ctx.uc_link = &main_ctx;
     makecontext(&j.ctx, gicp_fiber_entry, 0);
   }
+  // ---- groups: the live scans are dealt to up to kGicpGroups groups, each with its own stream and its own region
+  // of the task / sum buffers.  While the device serves one group's round the host runs the other groups' fibers
+  // (BFGS updates, the next requests), so neither side waits for the other; a scan's arithmetic does not depend on
+  // which group it is in.
+  struct Group {
+    std::vector<int> members;
+    cudaStream_t st = nullptr;
+    bool pending = false;
+    int live = 0, nf = 0;
+    int fdf_of[kMaxBatch];
+  };
   int live = 0;
   for (auto& jp : jobs) live += jp->finished ? 0 : 1;
+  const int ngroups = std::max(1, std::min(std::min(h->gicp_groups, kGicpGroups), live));
+  Group groups[kGicpGroups];
+  for (int i = 0, q = 0; i < B; ++i) {
+    if (jobs[i]->finished) continue;
+    Group& G = groups[q++ % ngroups];
+    G.members.push_back(i);
+    ++G.live;
+  }
+  CK(cudaStreamSynchronize(h->stream));  // the groups' streams start after the setup
+  for (int gi = 0; gi < ngroups; ++gi) {
+    if (!h->gicp_streams[gi]) CK(cudaStreamCreateWithFlags(&h->gicp_streams[gi], cudaStreamNonBlocking));
+    groups[gi].st = h->gicp_streams[gi];
+  }
   long rounds = 0;
   int rc_round = B2ICP_OK;
-  while (live > 0) {
-    // run every live fiber up to its next request
-    for (auto& jp : jobs) {
-      GicpJob& j = *jp;
+  double t_host = 0.0, t_wait = 0.0;
+  auto cuda_failed = [&](cudaError_t e) {
+    rc_round = B2ICP_ERR_CUDA;
+    h->err = std::string("GICP round: ") + cudaGetErrorString(e);
+    for (auto& jp : jobs) jp->rc = B2ICP_ERR_CUDA;  // every fiber unwinds at its next evaluation
+  };
+  // run the group's live fibers up to their next request, then put the round on the group's stream:
+  // correspondences first, then the evaluations, in stream order
+  auto advance_and_launch = [&](int gi) {
+    Group& G = groups[gi];
+    const auto t0 = now();
+    for (int i : G.members) {
+      GicpJob& j = *jobs[i];
       if (j.finished) continue;
       j.want_corr = j.want_fdf = false;
       g_entry_job = &j;
       swapcontext(&main_ctx, &j.ctx);
-      if (j.finished) --live;
+      if (j.finished) {
+        --G.live;
+        --live;
+      }
     }
-    // serve the round: correspondences first, then the evaluations, in stream order
+    const size_t off = (size_t)gi * kMaxBatch;
     int nc = 0, nf = 0;
-    int fdf_of[kMaxBatch];
-    for (int i = 0; i < B; ++i) {
+    for (int i : G.members) {
       GicpJob& j = *jobs[i];
       if (j.finished) continue;
       ScanSlot& s = slot(h, (size_t)i);
       GridSlot& g = gslot(h, s.grid);
       const int n = (int)s.src.n;
       if (j.want_corr) {
-        GicpCorrTask& t = h_corr[nc++];
+        GicpCorrTask& t = h_corr[off + nc++];
         t.g = g.view;
         t.src = s.src.dev();
         t.cov_src = s.cov.as<double>();
@@ -821,50 +874,76 @@ int run_gicp_batch(b2icp_handle* h, int B, const float* guesses) {
         t.pad = 0;
         t.a = j.iter;
       }
-      if (j.want_fdf) {
-        const int nblk = (n + kGicpThreads - 1) / kGicpThreads;
-        fdf_of[nf] = i;
-        GicpFdfTask& t = h_fdf[nf++];
-        t.src = s.src.dev();
-        t.tgt = g.pts;
-        t.corr_idx = s.corr_idx.as<int>();
-        t.mahal = s.mahal.as<double>();
-        (void)nblk;
-        t.partials = s.gicp_partials.as<double>();
-        t.sums = h->gicp_sums.as<double>() + (size_t)(nf - 1) * kGicpSums;
-        t.n = n;
-        t.pad = 0;
-        t.a = j.eval;
-      }
+      if (j.want_fdf) G.fdf_of[nf++] = i;
     }
-    if (nc == 0 && nf == 0) continue;
+    G.nf = nf;
+    G.pending = false;
+    if (nc == 0 && nf == 0) {
+      t_host += ms(t0, now());
+      return;
+    }
     ++rounds;
     cudaError_t e = cudaSuccess;
     if (nc) {
-      e = cudaMemcpyAsync(d_corr, h_corr, (size_t)nc * sizeof(GicpCorrTask), cudaMemcpyHostToDevice, h->stream);
-      gicp_corr_kernel<<<dim3((unsigned)((max_n + kSweepThreads - 1) / kSweepThreads), (unsigned)nc, 1), kSweepThreads, 0, h->stream>>>(d_corr);
+      e = cudaMemcpyAsync(d_corr + off, h_corr + off, (size_t)nc * sizeof(GicpCorrTask), cudaMemcpyHostToDevice, G.st);
+      gicp_corr_kernel<<<dim3((unsigned)((max_n + kSweepThreads - 1) / kSweepThreads), (unsigned)nc, 1), kSweepThreads, 0, G.st>>>(d_corr + off);
       h->launches += 1;
     }
-    if (nf && e == cudaSuccess) {
-      e = cudaMemcpyAsync(d_fdf, h_fdf, (size_t)nf * sizeof(GicpFdfTask), cudaMemcpyHostToDevice, h->stream);
-      gicp_fdf_kernel<<<dim3((unsigned)((max_n + kGicpThreads - 1) / kGicpThreads), (unsigned)nf, 1), kGicpThreads, 0, h->stream>>>(d_fdf);
-      gicp_sum_kernel<<<nf, 32, 0, h->stream>>>(d_fdf);
-      h->launches += 2;
-      if (e == cudaSuccess)  // the sums of the round's scans are contiguous: one read-back
-        e = cudaMemcpyAsync(h->h_gicp_partials, h->gicp_sums.p, (size_t)nf * kGicpSums * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    // evaluations: the tasks are kernel parameters and the 14 sums of every scan land in pinned host memory
+    // (mapped, written by the scan's last CTA): one launch per kGicpParamTasks scans, nothing else on the stream
+    for (int k0 = 0; k0 < nf && e == cudaSuccess; k0 += kGicpParamTasks) {
+      const int cnt = std::min(kGicpParamTasks, nf - k0);
+      GicpFdfBatch fb;
+      for (int k = 0; k < cnt; ++k) {
+        const int i = G.fdf_of[k0 + k];
+        ScanSlot& s = slot(h, (size_t)i);
+        GicpFdfTask& t = fb.t[k];
+        t.src = s.src.dev();
+        t.tgt = gslot(h, s.grid).pts;
+        t.corr_idx = s.corr_idx.as<int>();
+        t.mahal = s.mahal.as<double>();
+        t.partials = s.gicp_partials.as<double>();
+        t.sums = h->h_gicp_partials + (off + (size_t)(k0 + k)) * kGicpSums;
+        t.ticket = h->gicp_sums.as<unsigned int>() + i;
+        t.n = (int)s.src.n;
+        t.pad = 0;
+        t.a = jobs[i]->eval;
+      }
+      gicp_fdf_kernel<<<dim3((unsigned)((max_n + kGicpThreads - 1) / kGicpThreads), (unsigned)cnt, 1), kGicpThreads, 0, G.st>>>(fb);
+      h->launches += 1;
+      e = cudaGetLastError();
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) cuda_failed(e);
+    G.pending = true;
+    t_host += ms(t0, now());
+  };
+  auto collect = [&](int gi) {
+    Group& G = groups[gi];
+    const auto t0 = now();
+    cudaError_t e = cudaStreamSynchronize(G.st);
     if (e == cudaSuccess) e = cudaGetLastError();
-    if (e != cudaSuccess) {
-      rc_round = B2ICP_ERR_CUDA;
-      h->err = std::string("GICP round: ") + cudaGetErrorString(e);
-      for (auto& jp : jobs) jp->rc = B2ICP_ERR_CUDA;  // every fiber unwinds at its next evaluation
+    t_wait += ms(t0, now());
+    if (e != cudaSuccess) cuda_failed(e);
+    const size_t off = (size_t)gi * kMaxBatch;
+    for (int k = 0; k < G.nf; ++k)
+      std::memcpy(jobs[G.fdf_of[k]]->S, h->h_gicp_partials + (off + k) * kGicpSums, kGicpSums * sizeof(double));
+    G.pending = false;
+  };
+  for (int gi = 0; gi < ngroups; ++gi) advance_and_launch(gi);
+  for (bool any = true; any;) {
+    any = false;
+    for (int gi = 0; gi < ngroups; ++gi) {
+      Group& G = groups[gi];
+      if (!G.pending) continue;
+      collect(gi);
+      if (G.live > 0) advance_and_launch(gi);
+      any = any || G.pending;
     }
-    for (int k = 0; k < nf; ++k) std::memcpy(jobs[fdf_of[k]]->S, h->h_gicp_partials + (size_t)k * kGicpSums, kGicpSums * sizeof(double));
+    for (int gi = 0; gi < ngroups; ++gi) any = any || groups[gi].pending;
   }
   if (dbg)
-    fprintf(stderr, "[b2icp] GICP batch of %d: setup (grids + covariances) %.2f ms, %ld rounds %.2f ms\n", B,
-            ms(t_start, t_setup), rounds, ms(t_setup, now()));
+    fprintf(stderr, "[b2icp] GICP batch of %d in %d group(s): setup (grids + covariances) %.2f ms, %ld group rounds %.2f ms (host %.2f ms, waiting for the device %.2f ms)\n",
+            B, ngroups, ms(t_start, t_setup), rounds, ms(t_setup, now()), t_host, t_wait);
   h->gicp_rounds = rounds;
   h->gicp_evals = 0;
   int worst = rc_round;

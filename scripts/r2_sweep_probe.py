@@ -1,4 +1,4 @@
-"""Tuning probe (not the bench): per-iteration device time of the cooperative sweep on the bench workload
+"""Tuning probe (not the bench): per-iteration device time of the fused sweep on the bench workload
 (32 x 64k sweeps vs the 500k map, one synchronous batch) under different tuning knobs (environment variables
 read at b2icp_create)."""
 import os, sys, json, time
@@ -10,7 +10,7 @@ from icpslam_b200 import registration as R
 configs = [dict(a.split("=") for a in c.split(",") if a) for c in sys.argv[1:]] or [{}]
 map_xyzw, sweeps = bench.load_workload(0, 32)
 for cfg in configs:
-    for k in ("B2ICP_W", "B2ICP_JOIN", "B2ICP_PROBE", "B2ICP_SORT", "B2ICP_QPT"):
+    for k in ("B2ICP_NO_STAGE", "B2ICP_QPT", "B2ICP_QPT_SCHED", "B2ICP_MARGIN", "B2ICP_NO_GRAPH"):
         os.environ.pop(k, None)
     for k, v in cfg.items():
         os.environ["B2ICP_" + k] = v
