@@ -14,6 +14,38 @@
 #include <cuda_runtime.h>
 #include <ucontext.h>
 
+// Fiber switch of the GICP host loop (gicp_host.inl).  swapcontext() saves and restores the signal mask: two system
+// calls per switch, ~0.3 us each way, which was two thirds of the host time of a GICP round.  On x86-64 the switch
+// is six callee-saved registers and the stack pointer; elsewhere the ucontext path stays.
+#if defined(__x86_64__) && !defined(B2_FIBER_UCONTEXT) && !defined(__CUDA_ARCH__)
+#define B2_FIBER_ASM 1
+extern "C" void b2_fiber_switch(void** save_sp, void* load_sp);
+asm(R"(
+.text
+.p2align 4
+.globl b2_fiber_switch
+.hidden b2_fiber_switch
+.type b2_fiber_switch,@function
+b2_fiber_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size b2_fiber_switch,.-b2_fiber_switch
+)");
+#endif
+
 #include <algorithm>
 #include <cfloat>
 #include <chrono>
@@ -103,6 +135,11 @@ struct GridSlot {
   float mn[3], mx[3];
   double occupancy = 0;
   bool valid = false;
+  // what the last build of this slot settled on: a similar cloud (the next sweep of a stream) starts from that cell
+  // instead of the density estimate and usually needs no refinement pass
+  double hint_cell = 0, hint_ext[3] = {0, 0, 0};
+  size_t hint_n = 0;
+  bool bbox_known = false;  // mn / mx are already set by the caller (a second grid over the same cloud)
   void release() {
     for (DeviceBuf* b : {&tgt.raw, &sorted, &cell_start, &cell_of, &rank, &tile_sums, &bbox, &cov}) b->release();
   }
@@ -315,23 +352,28 @@ int rings_for_bound(const b2icp_handle* h, double min_cell) {
 // ---- K1: neighbour-grid build, split in phases so that a batch needs two host syncs in total ------
 // phase A: bounding boxes of `count` clouds -> h->h_bbox[0..count)
 int grids_bbox(b2icp_handle* h, GridSlot* const* g, const size_t* n, int count) {
+  bool any = false;
   for (int i = 0; i < count; ++i) {
     CK(g[i]->bbox.ensure(sizeof(BBox)));
+    if (g[i]->bbox_known) continue;
+    any = true;
     const int blocks = (int)((n[i] + 255) / 256);
     bbox_init<<<1, 32, 0, h->stream>>>(g[i]->bbox.as<BBox>());
     bbox_kernel<<<std::min(blocks, 148 * 8), 256, 0, h->stream>>>(g[i]->pts, (int)n[i], g[i]->bbox.as<BBox>());
     h->launches += 2;
     CK(cudaMemcpyAsync(&h->h_bbox[i], g[i]->bbox.p, sizeof(BBox), cudaMemcpyDeviceToHost, h->stream));
   }
-  CK(cudaStreamSynchronize(h->stream));
+  if (any) CK(cudaStreamSynchronize(h->stream));
   for (int i = 0; i < count; ++i) {
-    if (h->h_bbox[i].nonfinite) return fail(h, B2ICP_ERR_NONFINITE_INPUT, "target cloud holds non-finite coordinates");
     double ext[3];
-    for (int d = 0; d < 3; ++d) {
-      g[i]->mn[d] = ord2f(h->h_bbox[i].mn[d]);
-      g[i]->mx[d] = ord2f(h->h_bbox[i].mx[d]);
-      ext[d] = (double)g[i]->mx[d] - (double)g[i]->mn[d];
+    if (!g[i]->bbox_known) {
+      if (h->h_bbox[i].nonfinite) return fail(h, B2ICP_ERR_NONFINITE_INPUT, "target cloud holds non-finite coordinates");
+      for (int d = 0; d < 3; ++d) {
+        g[i]->mn[d] = ord2f(h->h_bbox[i].mn[d]);
+        g[i]->mx[d] = ord2f(h->h_bbox[i].mx[d]);
+      }
     }
+    for (int d = 0; d < 3; ++d) ext[d] = (double)g[i]->mx[d] - (double)g[i]->mn[d];
     const double emax = std::max(ext[0], std::max(ext[1], ext[2]));
     // density-based cell: ~kTargetOccupancy points per cell if the cloud filled its box uniformly;
     // axes thinner than 1e-6 of the largest extent (planar scans) are left out of the estimate
@@ -347,6 +389,11 @@ int grids_bbox(b2icp_handle* h, GridSlot* const* g, const size_t* n, int count) 
     const double r = h->params.max_correspondence_distance;
     const bool bounded = r > 0 && std::isfinite(r) && r < 1e8;
     if (bounded) cell = std::min(cell, 0.5 * r);
+    if (g[i]->hint_cell > 0 && (double)n[i] > 0.8 * (double)g[i]->hint_n && (double)n[i] < 1.25 * (double)g[i]->hint_n) {
+      bool similar = true;  // same kind of cloud as the one this slot indexed last (cell size is a speed matter only)
+      for (int d = 0; d < 3; ++d) similar = similar && std::fabs(ext[d] - g[i]->hint_ext[d]) <= 0.25 * std::max(emax, 1e-9);
+      if (similar) cell = bounded ? std::min(g[i]->hint_cell, 0.5 * r) : g[i]->hint_cell;
+    }
     if (h->params.grid_cell > 0) cell = h->params.grid_cell;
     if (g[i]->force_cell > 0) cell = g[i]->force_cell;
     if (!(cell > 0) || !std::isfinite(cell)) cell = 1.0;
@@ -417,11 +464,14 @@ int build_grids(b2icp_handle* h, GridSlot* const* g, const size_t* n, int count)
   std::vector<int> todo(count);
   for (int i = 0; i < count; ++i) todo[i] = i;
   for (int attempt = 0; attempt < 3 && !todo.empty(); ++attempt) {
+    bool refinable = false;  // a given cell edge is final: nothing to read back, the build stays asynchronous
+    for (int i : todo) refinable = refinable || !(g[i]->force_cell > 0);
     for (int i : todo) {
       rc = grid_enqueue_build(h, g[i], n[i]);
       if (rc) return rc;
-      CK(cudaMemcpyAsync(&h->h_bbox[i], g[i]->bbox.p, sizeof(BBox), cudaMemcpyDeviceToHost, h->stream));
+      if (refinable) CK(cudaMemcpyAsync(&h->h_bbox[i], g[i]->bbox.p, sizeof(BBox), cudaMemcpyDeviceToHost, h->stream));
     }
+    if (!refinable) break;
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());
     std::vector<int> again;
@@ -437,7 +487,12 @@ int build_grids(b2icp_handle* h, GridSlot* const* g, const size_t* n, int count)
     }
     todo.swap(again);
   }
-  for (int i = 0; i < count; ++i) g[i]->valid = true;
+  for (int i = 0; i < count; ++i) {
+    g[i]->valid = true;
+    g[i]->hint_cell = g[i]->cell;
+    g[i]->hint_n = n[i];
+    for (int d = 0; d < 3; ++d) g[i]->hint_ext[d] = (double)g[i]->mx[d] - (double)g[i]->mn[d];
+  }
   return B2ICP_OK;
 }
 

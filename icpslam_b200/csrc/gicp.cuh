@@ -84,40 +84,42 @@ __device__ __forceinline__ double norm3r(const double* a) {
 }
 
 // U of the SVD A = U diag(s) V^T (s descending), by the fixed one-sided Jacobi recipe of the arithmetic
-// definition: pairs (0,1), (0,2), (1,2); rotate unless ga == 0 or |ga| <= 1e-17 sqrt(al be);
+// definition: pairs (0,1), (0,2), (1,2); rotate unless ga == 0 or |ga| <= 1e-15 sqrt(al be)
+// (where a rotation stops changing an fp64 column; Eigen::JacobiSVD itself stops at 2 eps);
 // zeta = (be - al) / (2 ga); t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)); c = 1 / sqrt(1 + t^2); s = c t.
-__device__ void svd3_u(const double* A, double* U) {
-  double B[9];
+// one sweep over the pairs (0,1), (0,2), (1,2) of the recipe; false = no pair was rotated (converged)
+__device__ __forceinline__ bool svd3_sweep(double* B) {
+  bool rotated = false;
 #pragma unroll
-  for (int i = 0; i < 9; ++i) B[i] = A[i];
-  for (int sweep = 0; sweep < 60; ++sweep) {
-    bool rotated = false;
+  for (int pq = 0; pq < 3; ++pq) {
+    const int p = (pq == 2) ? 1 : 0;
+    const int q = (pq == 0) ? 1 : 2;
+    double al = 0, be = 0, ga = 0;
 #pragma unroll
-    for (int pq = 0; pq < 3; ++pq) {
-      const int p = (pq == 2) ? 1 : 0;
-      const int q = (pq == 0) ? 1 : 2;
-      double al = 0, be = 0, ga = 0;
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        al = dadd(al, dmul(B[3 * i + p], B[3 * i + p]));
-        be = dadd(be, dmul(B[3 * i + q], B[3 * i + q]));
-        ga = dadd(ga, dmul(B[3 * i + p], B[3 * i + q]));
-      }
-      if (ga == 0.0 || fabs(ga) <= dmul(1e-17, __dsqrt_rn(dmul(al, be)))) continue;
-      rotated = true;
-      const double zeta = ddiv(dsub(be, al), dmul(2.0, ga));
-      const double t = ddiv(zeta >= 0 ? 1.0 : -1.0, dadd(fabs(zeta), __dsqrt_rn(dadd(1.0, dmul(zeta, zeta)))));
-      const double c = ddiv(1.0, __dsqrt_rn(dadd(1.0, dmul(t, t))));
-      const double sn = dmul(c, t);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const double bp = B[3 * i + p], bq = B[3 * i + q];
-        B[3 * i + p] = dsub(dmul(c, bp), dmul(sn, bq));
-        B[3 * i + q] = dadd(dmul(sn, bp), dmul(c, bq));
-      }
+    for (int i = 0; i < 3; ++i) {
+      al = dadd(al, dmul(B[3 * i + p], B[3 * i + p]));
+      be = dadd(be, dmul(B[3 * i + q], B[3 * i + q]));
+      ga = dadd(ga, dmul(B[3 * i + p], B[3 * i + q]));
     }
-    if (!rotated) break;
+    if (ga == 0.0 || fabs(ga) <= dmul(1e-15, __dsqrt_rn(dmul(al, be)))) continue;
+    rotated = true;
+    const double zeta = ddiv(dsub(be, al), dmul(2.0, ga));
+    const double t = ddiv(zeta >= 0 ? 1.0 : -1.0, dadd(fabs(zeta), __dsqrt_rn(dadd(1.0, dmul(zeta, zeta)))));
+    const double c = ddiv(1.0, __dsqrt_rn(dadd(1.0, dmul(t, t))));
+    const double sn = dmul(c, t);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const double bp = B[3 * i + p], bq = B[3 * i + q];
+      B[3 * i + p] = dsub(dmul(c, bp), dmul(sn, bq));
+      B[3 * i + q] = dadd(dmul(sn, bp), dmul(c, bq));
+    }
   }
+  return rotated;
+}
+constexpr int kSvdMaxSweeps = 60;
+
+// the rest of the recipe once the sweeps are over: column norms, stable descending order, rank completion
+__device__ void svd3_finish(const double* B, double* U) {
   double nrm[3];
 #pragma unroll
   for (int j = 0; j < 3; ++j)
@@ -160,6 +162,14 @@ __device__ void svd3_u(const double* A, double* U) {
   for (int j = 0; j < 3; ++j)
     for (int i = 0; i < 3; ++i) U[3 * i + j] = u[j][i];
 }
+__device__ void svd3_u(const double* A, double* U) {
+  double B[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) B[i] = A[i];
+  for (int sweep = 0; sweep < kSvdMaxSweeps; ++sweep)
+    if (!svd3_sweep(B)) break;
+  svd3_finish(B, U);
+}
 
 // ---- K5: k nearest neighbours + regularised covariance ---------------------------------------------
 // One thread per point of `cloud` (original order); `g` is the grid built over the same cloud.  The k best
@@ -184,8 +194,9 @@ __device__ __forceinline__ void knn_scan(const float4* __restrict__ pts, int s, 
   }
 }
 
+// first half of computeCovariances for one point: the raw covariance of its k neighbours (9 doubles, row-major)
 __device__ __forceinline__ void cov_from_keys(const float4* __restrict__ cloud, const unsigned long long* keys, int k,
-                                              double eps, double* __restrict__ out9) {
+                                              double* __restrict__ out9) {
   double mean[3] = {0, 0, 0};
   double c00 = 0, c10 = 0, c11 = 0, c20 = 0, c21 = 0, c22 = 0;
   for (int j = 0; j < k; ++j) {
@@ -212,8 +223,11 @@ __device__ __forceinline__ void cov_from_keys(const float4* __restrict__ cloud, 
   C[1] = C[3];
   C[2] = C[6];
   C[5] = C[7];
-  double U[9];
-  svd3_u(C, U);
+  for (int i = 0; i < 9; ++i) out9[i] = C[i];
+}
+
+// second half of computeCovariances for one point: U of the covariance's SVD, eigenvalues replaced by (1, 1, eps)
+__device__ __forceinline__ void cov_regularise(const double* U, double eps, double* __restrict__ out9) {
   double o[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   for (int col = 0; col < 3; ++col) {
     const double v = col == 2 ? eps : 1.0;
@@ -292,7 +306,7 @@ __device__ __forceinline__ void knn_cov_point(const KnnTask& t, int task_id, int
     unresolved_list[atomicAdd(unresolved_count, 1u)] = make_int2(task_id, i);
     return;
   }
-  cov_from_keys(cloud, keys, k, eps, t.cov + (size_t)9 * i);
+  cov_from_keys(cloud, keys, k, t.cov + (size_t)9 * i);
 }
 
 
@@ -368,9 +382,58 @@ __global__ void __launch_bounds__(kKnnFbThreads) knn_cov_fallback(const KnnTask*
     if (threadIdx.x == 0) {
       unsigned long long out[kMaxK];
       for (int j = 0; j < k; ++j) out[j] = s_keys[j];
-      cov_from_keys(t.cloud, out, k, eps, t.cov + (size_t)9 * i);
+      cov_from_keys(t.cloud, out, k, t.cov + (size_t)9 * i);
     }
     __syncthreads();
+  }
+}
+
+// Last stage of the covariances: every raw covariance left in `cov` by the three passes above becomes
+// U diag(1, 1, eps) U^T in place.  The Jacobi recipe needs anything from a few sweeps to its cap of 60 depending on
+// the matrix, so a thread per point leaves most lanes of a warp waiting for its slowest matrix (ncu: 8 of 32 lanes
+// active, 47 % of the covariance kernel's instructions).  Here the lanes of a warp advance their matrices ONE sweep at a
+// time and a lane whose matrix has converged finishes it and takes the next point of its cloud from a counter
+// (warp-aggregated atomic), so the sweep code always runs on a full warp.  The arithmetic of a point is the same
+// sequence of operations as svd3_u().
+__global__ void __launch_bounds__(128) cov_svd_kernel(const KnnTask* __restrict__ tasks, double eps,
+                                                      unsigned int* __restrict__ counters) {
+  const KnnTask& t = tasks[blockIdx.y];
+  unsigned int* ctr = counters + blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const unsigned int n = (unsigned int)t.n;
+  double B[9];
+  unsigned int i = 0;
+  int sweep = 0;
+  bool active = false, done = false;
+  for (;;) {
+    const unsigned int need = __ballot_sync(0xFFFFFFFFu, !active && !done);
+    if (need) {
+      const int leader = __ffs(need) - 1;
+      unsigned int base = 0;
+      if (lane == leader) base = atomicAdd(ctr, (unsigned int)__popc(need));
+      base = __shfl_sync(0xFFFFFFFFu, base, leader);
+      if (!active && !done) {
+        i = base + (unsigned int)__popc(need & ((1u << lane) - 1u));
+        if (i < n) {
+          const double* C = t.cov + (size_t)9 * i;
+#pragma unroll
+          for (int e = 0; e < 9; ++e) B[e] = C[e];
+          sweep = 0;
+          active = true;
+        } else {
+          done = true;
+        }
+      }
+    }
+    if (__all_sync(0xFFFFFFFFu, done)) break;
+    bool rotated = false;
+    if (active) rotated = svd3_sweep(B);
+    if (active && (!rotated || ++sweep == kSvdMaxSweeps)) {
+      double U[9];
+      svd3_finish(B, U);
+      cov_regularise(U, eps, t.cov + (size_t)9 * i);
+      active = false;
+    }
   }
 }
 

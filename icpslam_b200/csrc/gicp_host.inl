@@ -9,13 +9,41 @@
 //
 // Batching: the recursion of ONE scan is a chain of ~100 dependent evaluations, each a few microseconds of device
 // work behind a launch and a read-back — latency, not throughput.  A batch therefore runs every scan's recursion
-// as its own FIBER (ucontext): the unmodified blocking code of one scan runs until it needs an evaluation, posts
+// as its own FIBER (a private stack and a register switch): the unmodified blocking code of one scan runs until it needs an evaluation, posts
 // its request (new correspondences and / or one cost-functor evaluation) and yields; when every live fiber has
 // yielded, the coordinator serves the whole round with one launch per kernel (blockIdx.y = scan), one 14-double
 // read-back per scan and ONE synchronisation, then resumes the fibers.  A scan's arithmetic does not depend on
 // which other scans share its rounds: results are bit-identical to the one-scan-at-a-time path of round 1.
 struct GicpJob;
 void gicp_yield(GicpJob* job);
+
+// One execution context of the host loop: the coordinator's or a scan's fiber.
+#ifdef B2_FIBER_ASM
+struct FiberCtx {
+  void* sp = nullptr;
+};
+inline void fiber_switch(FiberCtx& from, FiberCtx& to) { b2_fiber_switch(&from.sp, to.sp); }
+// first switch into `c` "returns" into entry() on the given stack (entry never returns: it switches away for good)
+inline void fiber_make(FiberCtx& c, FiberCtx&, char* stack, size_t size, void (*entry)()) {
+  void** sp = reinterpret_cast<void**>((reinterpret_cast<uintptr_t>(stack) + size) & ~(uintptr_t)15);
+  *--sp = nullptr;                              // where entry's return address would be
+  *--sp = reinterpret_cast<void*>(entry);       // popped by the switch's `ret`; entry then sees rsp = 8 mod 16
+  for (int i = 0; i < 6; ++i) *--sp = nullptr;  // rbp rbx r12 r13 r14 r15
+  c.sp = sp;
+}
+#else
+struct FiberCtx {
+  ucontext_t uc;
+};
+inline void fiber_switch(FiberCtx& from, FiberCtx& to) { swapcontext(&from.uc, &to.uc); }
+inline void fiber_make(FiberCtx& c, FiberCtx& back, char* stack, size_t size, void (*entry)()) {
+  getcontext(&c.uc);
+  c.uc.uc_stack.ss_sp = stack;
+  c.uc.uc_stack.ss_size = size;
+  c.uc.uc_link = &back.uc;
+  makecontext(&c.uc, entry, 0);
+}
+#endif
 
 struct GicpHostFunctor {
   b2icp_handle* h;
@@ -428,28 +456,10 @@ int compute_covariances_batch(b2icp_handle* h, GridSlot* const* gs, const size_t
     max_n = std::max(max_n, n[i]);
     total += n[i];
   }
-  // the coarse grids: same clouds, four times the cell edge
-  std::vector<GridSlot*> cg((size_t)count);
-  std::vector<size_t> cn(n, n + count);
-  for (int i = 0; i < count; ++i) {
-    GridSlot& c = gslot(h, (size_t)(2 * kMaxBatch + 16 + i));
-    c.pts = gs[i]->pts;
-    c.force_cell = 4.0 * gs[i]->cell;
-    cg[(size_t)i] = &c;
-  }
-  const bool dbg = getenv("B2ICP_GICP_DEBUG") != nullptr;
-  const auto t0 = std::chrono::steady_clock::now();
-  int rc = build_grids(h, cg.data(), cn.data(), count);
-  if (rc) return rc;
-  if (dbg) {
-    cudaStreamSynchronize(h->stream);
-    fprintf(stderr, "[b2icp]   covariances of %d cloud(s): coarse grids %.2f ms\n", count,
-            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
-  }
   CK(h->knn_tasks.ensure((size_t)2 * count * sizeof(KnnTask)));
   CK(h->unres_list.ensure(total * sizeof(int2)));
   CK(h->knn_list2.ensure(total * sizeof(int2)));
-  CK(h->knn_counts.ensure(2 * sizeof(unsigned int)));
+  CK(h->knn_counts.ensure((2 + (size_t)kMaxBatch) * sizeof(unsigned int)));  // two list lengths + one point counter per cloud
   std::vector<KnnTask> tasks((size_t)2 * count);
   for (int i = 0; i < count; ++i) {
     KnnTask& f = tasks[(size_t)i];
@@ -458,21 +468,44 @@ int compute_covariances_batch(b2icp_handle* h, GridSlot* const* gs, const size_t
     f.cov = covs[i]->as<double>();
     f.n = (int)n[i];
     f.pad = 0;
-    tasks[(size_t)(count + i)] = f;
+  }
+  // the coarse grids of the second pass: same clouds, same boxes, four times the cell edge.  Box and cell are
+  // given, so their builds need no read-back and stay asynchronous in front of the first pass.
+  std::vector<GridSlot*> cg((size_t)count);
+  std::vector<size_t> cn(n, n + count);
+  for (int i = 0; i < count; ++i) {
+    GridSlot& c = gslot(h, (size_t)(2 * kMaxBatch + 16 + i));
+    c.pts = gs[i]->pts;
+    c.force_cell = 4.0 * gs[i]->cell;
+    for (int d = 0; d < 3; ++d) {
+      c.mn[d] = gs[i]->mn[d];
+      c.mx[d] = gs[i]->mx[d];
+    }
+    c.bbox_known = true;
+    cg[(size_t)i] = &c;
+  }
+  int rc = build_grids(h, cg.data(), cn.data(), count);
+  if (rc) return rc;
+  for (int i = 0; i < count; ++i) {
+    tasks[(size_t)(count + i)] = tasks[(size_t)i];
     tasks[(size_t)(count + i)].g = cg[(size_t)i]->view;
   }
-  // (pageable source: the copy is staged by the driver before the call returns)
-  CK(cudaMemcpyAsync(h->knn_tasks.p, tasks.data(), tasks.size() * sizeof(KnnTask), cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemsetAsync(h->knn_counts.p, 0, 2 * sizeof(unsigned int), h->stream));
   const KnnTask* fine = h->knn_tasks.as<KnnTask>();
   const KnnTask* coarse = fine + count;
   unsigned int* c1 = h->knn_counts.as<unsigned int>();
   unsigned int* c2 = c1 + 1;
+  // (pageable source: the copy is staged by the driver before the call returns)
+  CK(cudaMemcpyAsync(h->knn_tasks.p, tasks.data(), tasks.size() * sizeof(KnnTask), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemsetAsync(h->knn_counts.p, 0, (2 + (size_t)kMaxBatch) * sizeof(unsigned int), h->stream));
   knn_cov_kernel<<<dim3((unsigned)((max_n + 127) / 128), (unsigned)count, 1), 128, 0, h->stream>>>(fine, k, h->params.gicp_epsilon, 6,
                                                                                                  h->unres_list.as<int2>(), c1);
   knn_cov_list_kernel<<<148 * 8, 128, 0, h->stream>>>(coarse, k, h->params.gicp_epsilon, 8, h->unres_list.as<int2>(), c1,
                                                       h->knn_list2.as<int2>(), c2);
   knn_cov_fallback<<<148 * 4, kKnnFbThreads, 0, h->stream>>>(fine, k, h->params.gicp_epsilon, h->knn_list2.as<int2>(), c2);
+  // raw covariances -> U diag(1, 1, eps) U^T, lanes load-balanced over the points of each cloud
+  const unsigned int sx = (unsigned int)std::max<size_t>(1, std::min<size_t>((max_n + 127) / 128, (size_t)(148 * 16 + count - 1) / (size_t)count));
+  cov_svd_kernel<<<dim3(sx, (unsigned)count, 1), 128, 0, h->stream>>>(fine, h->params.gicp_epsilon, c1 + 2);
+  h->launches += 1;
   h->launches += 3;
   return B2ICP_OK;
 }
@@ -498,11 +531,11 @@ struct GicpJob {
   int rc = B2ICP_OK;
   long evals = 0;
   // fiber
-  ucontext_t ctx, *back = nullptr;
+  FiberCtx ctx, *back = nullptr;
   std::vector<char> stack;
 };
 
-void gicp_yield(GicpJob* job) { swapcontext(&job->ctx, job->back); }
+void gicp_yield(GicpJob* job) { fiber_switch(job->ctx, *job->back); }
 
 void GicpHostFunctor::fdf(const double* x, double* f, double* g) {
   ++evals;
@@ -778,7 +811,7 @@ int run_gicp_batch(b2icp_handle* h, int B, const float* guesses) {
 
   // ---- one fiber per scan
   std::vector<std::unique_ptr<GicpJob>> jobs;
-  ucontext_t main_ctx;
+  FiberCtx main_ctx;
   for (int i = 0; i < B; ++i) {
     jobs.emplace_back(new GicpJob());
     GicpJob& j = *jobs.back();
@@ -796,11 +829,7 @@ int run_gicp_batch(b2icp_handle* h, int B, const float* guesses) {
     }
     j.stack.resize(256 * 1024);
     j.back = &main_ctx;
-    getcontext(&j.ctx);
-    j.ctx.uc_stack.ss_sp = j.stack.data();
-    j.ctx.uc_stack.ss_size = j.stack.size();
-    j.ctx.uc_link = &main_ctx;
-    makecontext(&j.ctx, gicp_fiber_entry, 0);
+    fiber_make(j.ctx, main_ctx, j.stack.data(), j.stack.size(), gicp_fiber_entry);
   }
   // ---- groups: the live scans are dealt to up to kGicpGroups groups, each with its own stream and its own region
   // of the task / sum buffers.  While the device serves one group's round the host runs the other groups' fibers
@@ -846,7 +875,7 @@ int run_gicp_batch(b2icp_handle* h, int B, const float* guesses) {
       if (j.finished) continue;
       j.want_corr = j.want_fdf = false;
       g_entry_job = &j;
-      swapcontext(&main_ctx, &j.ctx);
+      fiber_switch(main_ctx, j.ctx);
       if (j.finished) {
         --G.live;
         --live;

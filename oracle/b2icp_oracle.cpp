@@ -263,7 +263,10 @@ inline double det3(const double* M) {
          M[2] * (M[3] * M[7] - M[4] * M[6]);
 }
 
-void svd3(const double* A, double* U, double* s, double* V) {
+/* `skip`: a pair whose |cos| is at or below it is left alone.  1e-17 (below one ulp: the sweeps run until rounding
+ * happens to produce an exact zero, or to the cap) for the Umeyama solve; 1e-15 for the GICP covariances, which is
+ * where a rotation stops changing an fp64 column and still tighter than Eigen::JacobiSVD's own 2 eps. */
+void svd3_skip(const double* A, double* U, double* s, double* V, double skip) {
   double B[9], W[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
   std::memcpy(B, A, sizeof(B));
   for (int sweep = 0; sweep < 60; ++sweep) {
@@ -276,7 +279,7 @@ void svd3(const double* A, double* U, double* s, double* V) {
           be += B[3 * i + q] * B[3 * i + q];
           ga += B[3 * i + p] * B[3 * i + q];
         }
-        if (ga == 0.0 || std::fabs(ga) <= 1e-17 * std::sqrt(al * be)) continue;
+        if (ga == 0.0 || std::fabs(ga) <= skip * std::sqrt(al * be)) continue;
         rotated = true;
         double zeta = (be - al) / (2.0 * ga);
         double t = (zeta >= 0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
@@ -336,6 +339,7 @@ void svd3(const double* A, double* U, double* s, double* V) {
       V[3 * i + j] = v[j][i];
     }
 }
+void svd3(const double* A, double* U, double* s, double* V) { svd3_skip(A, U, s, V, 1e-17); }
 
 /* Eigen::umeyama(src, dst, with_scaling=false) as called by
  * pcl::registration::TransformationEstimationSVD (Appendix A.3) from the 16 running sums
@@ -629,6 +633,11 @@ int b2o_umeyama(const float* src, const float* dst, size_t n, double* T16) {
 
 int b2o_svd3(const double* A9, double* U9, double* s3, double* V9) {
   svd3(A9, U9, s3, V9);
+  return B2ICP_OK;
+}
+
+int b2o_svd3_cov(const double* A9, double* U9, double* s3, double* V9) {
+  svd3_skip(A9, U9, s3, V9, 1e-15);
   return B2ICP_OK;
 }
 

@@ -63,6 +63,8 @@ size_t b2o_gicp_trace_count(void);
 int b2o_umeyama(const float* src_xyzw, const float* dst_xyzw, size_t n, double* T16);
 /* 3x3 SVD A = U diag(s) V^T (row-major 3x3, s descending; JacobiSVD FullU|FullV semantics). */
 int b2o_svd3(const double* A9, double* U9, double* s3, double* V9);
+/* the same recipe with the pair-skip threshold of the GICP covariances (|cos| <= 1e-15) */
+int b2o_svd3_cov(const double* A9, double* U9, double* s3, double* V9);
 
 /* Registration::align (Appendix A.1) with the solver selected by p->mode:
  * P2P_SVD = IterativeClosestPoint (A.3), GICP_BFGS = GeneralizedIterativeClosestPoint (A.2/A.4).

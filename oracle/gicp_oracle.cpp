@@ -603,7 +603,7 @@ int compute_covariances(const float* cloud, size_t n, const void* tree, int k, d
     C[2] = C[6];
     C[5] = C[7];
     double U[9], s[3], V[9];
-    b2o_svd3(C, U, s, V);
+    b2o_svd3_cov(C, U, s, V);
     double* out = cov9 + 9 * i;
     for (int e = 0; e < 9; ++e) out[e] = 0;
     for (int col = 0; col < 3; ++col) {
