@@ -59,8 +59,13 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) icp_sweep_p2p(co
   __shared__ float sT[kWarps][16];
   __shared__ unsigned short wl_id[kWarps][kWarpSlab];  // work list of the warp: query index inside its slab
   const ScanTask& t = tasks[blockIdx.y];
+  // the fields the row loop uses, read once: the loop stores through float4 pointers, which the compiler has to
+  // assume may alias the task record and would otherwise reload them after every store
+  const int tn = t.n;
+  float4* const tcur = t.cur;
+  const float4* const tsrc = t.src;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nslab = (t.n + kWarpSlab - 1) / kWarpSlab;
+  const int nslab = (tn + kWarpSlab - 1) / kWarpSlab;
   const int slab = blockIdx.x * kWarps + warp;
   if (slab >= nslab) return;
   IcpState* st = t.state;
@@ -84,13 +89,13 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) icp_sweep_p2p(co
   for (int qi = 0; qi < QPT; ++qi) {
     const int i = base + qi * 32 + lane;
     bool need = false;
-    if (i < t.n) {
+    if (i < tn) {
       float4 p, c[kCacheK];
       float lb = 0.0f;
       if (first) {
-        p = __ldg(t.src + i);
+        p = __ldg(tsrc + i);
       } else {  // independent coalesced loads
-        p = ld_stream(t.cur + i);
+        p = ld_stream(tcur + i);
 #pragma unroll
         for (int k = 0; k < kCacheK; ++k) c[k] = ld_stream(cand[k] + i);
         lb = p.w;  // the bound travels in the running point's fourth component
@@ -135,7 +140,7 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) icp_sweep_p2p(co
           need = true;
         }
       }
-      st_stream(t.cur + i, q);
+      st_stream(tcur + i, q);
     }
     const unsigned bal = __ballot_sync(0xFFFFFFFFu, need);
     if (need) wl_id[warp][wc + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)(qi * 32 + lane);
@@ -146,7 +151,7 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) icp_sweep_p2p(co
   // ---- phase B
   for (int e = lane; e < wc; e += 32) {
     const int i = base + (int)wl_id[warp][e];
-    const float4 q = t.cur[i];
+    const float4 q = tcur[i];
     // search radius: the nearer cached candidate (the list keeps ids only, so that long slabs fit in shared
     // memory; the two points are L2-hot), or the probe when there is none
     float seed = INFINITY;
@@ -167,7 +172,7 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) icp_sweep_p2p(co
     st_stream(cand[0] + i, m0);
 #pragma unroll
     for (int k = 1; k < kCacheK; ++k) st_stream(cand[k] + i, top.p[k] >= 0 ? __ldg(t.grid.pts + top.p[k]) : none);
-    st_stream(t.cur + i, make_float4(q.x, q.y, q.z, top3_bound(top, lrest)));
+    st_stream(tcur + i, make_float4(q.x, q.y, q.z, top3_bound(top, lrest)));
     const float d2 = key_d2(top.k0);
     if ((top.k0 != kInfKey) && !((double)d2 > cfg.max2)) accumulate_pair(acc, q, m0, d2);
   }
