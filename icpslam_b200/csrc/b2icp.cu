@@ -276,7 +276,8 @@ struct b2icp_handle {
   size_t h_gicp_tasks_cap = 0;
   DeviceBuf gicp_tasks, gicp_sums, knn_tasks, knn_list2, knn_counts;
   long gicp_evals = 0, gicp_rounds = 0;
-  int gicp_groups = 2;  // B2ICP_GICP_GROUPS (tuning only)
+  int gicp_groups = 4;  // B2ICP_GICP_GROUPS (tuning only)
+  int fitness_rings = kUnboundedRings;  // B2ICP_FITNESS_RINGS (tuning only): ring budget of getFitnessScore's search
   cudaStream_t gicp_streams[kGicpGroups] = {nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -784,7 +785,7 @@ int enqueue_fitness(b2icp_handle* h, int i, double max_range) {
   CK(h->unres_list.ensure(n * sizeof(int)));
   zero_counter<<<1, 1, 0, h->stream>>>(h->unres_count.as<unsigned int>());
   dim3 grid((unsigned)((n + kSweepThreads - 1) / kSweepThreads), 1, 1);
-  fitness_kernel<<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>() + i, kUnboundedRings,
+  fitness_kernel<<<grid, kSweepThreads, 0, h->stream>>>(h->tasks.as<ScanTask>() + i, h->fitness_rings,
                                                         h->unres_list.as<int>(), h->unres_count.as<unsigned int>(),
                                                         h->query.as<float4>(), h->q_idx.as<int>(), h->q_d2.as<float>());
   {
@@ -1129,6 +1130,7 @@ int b2icp_create(const b2icp_params* p, b2icp_handle** out) {
   if (const char* e = getenv("B2ICP_QPT")) h->qpt_override = atoi(e);
   if (getenv("B2ICP_NO_GRAPH")) h->use_graphs = false;
   if (const char* e = getenv("B2ICP_GICP_GROUPS")) h->gicp_groups = std::max(1, atoi(e));
+  if (const char* e = getenv("B2ICP_FITNESS_RINGS")) h->fitness_rings = std::max(1, atoi(e));
   if (getenv("B2ICP_NO_TINY")) h->use_tiny = false;
   if (const char* e = getenv("B2ICP_W")) h->w_override = atoi(e);
   if (const char* e = getenv("B2ICP_JOIN")) h->join_d = atoi(e);

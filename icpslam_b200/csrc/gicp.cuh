@@ -176,30 +176,50 @@ __device__ void svd3_u(const double* A, double* U) {
 // (d2, index) keys are kept sorted in a per-thread array; rings of cells are visited until the distance to
 // the outside of the visited block exceeds the k-th best distance.  Points that exhaust `max_rings` are
 // queued for the exhaustive fallback (same arithmetic, every point scanned).
+// KS > 0: k is the compile-time constant KS, the list lives in registers (every index static) and an insertion is a
+// branch-free bubble of the candidate through the list — the same straight-line code for every lane.  KS == 0: k is
+// a run-time value, the list is a local-memory array shifted by a loop (the general path).
+template <int KS>
 __device__ __forceinline__ void knn_offer(unsigned long long* keys, int k, unsigned long long c) {
-  if (c >= keys[k - 1]) return;
-  int p = k - 1;
-  while (p > 0 && keys[p - 1] > c) {
-    keys[p] = keys[p - 1];
-    --p;
+  if (KS > 0) {
+    if (c >= keys[KS - 1]) return;
+#pragma unroll
+    for (int j = 0; j < KS; ++j) {
+      const bool lt = c < keys[j];
+      const unsigned long long hi = lt ? keys[j] : c;
+      keys[j] = lt ? c : keys[j];
+      c = hi;
+    }
+  } else {
+    if (c >= keys[k - 1]) return;
+    int p = k - 1;
+    while (p > 0 && keys[p - 1] > c) {
+      keys[p] = keys[p - 1];
+      --p;
+    }
+    keys[p] = c;
   }
-  keys[p] = c;
 }
 
+template <int KS>
 __device__ __forceinline__ void knn_scan(const float4* __restrict__ pts, int s, int e, float qx, float qy, float qz,
                                          unsigned long long* keys, int k) {
   for (int j = s; j < e; ++j) {
     const float4 p = __ldg(pts + j);
-    knn_offer(keys, k, pack_key(sqdist3(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w)));
+    knn_offer<KS>(keys, k, pack_key(sqdist3(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w)));
   }
 }
 
 // first half of computeCovariances for one point: the raw covariance of its k neighbours (9 doubles, row-major)
-__device__ __forceinline__ void cov_from_keys(const float4* __restrict__ cloud, const unsigned long long* keys, int k,
+template <int KS>
+__device__ __forceinline__ void cov_from_keys(const float4* __restrict__ cloud, const unsigned long long* keys, int k_,
                                               double* __restrict__ out9) {
+  const int k = KS > 0 ? KS : k_;
   double mean[3] = {0, 0, 0};
   double c00 = 0, c10 = 0, c11 = 0, c20 = 0, c21 = 0, c22 = 0;
-  for (int j = 0; j < k; ++j) {
+#pragma unroll
+  for (int j = 0; j < (KS > 0 ? KS : kMaxK); ++j) {
+    if (KS == 0 && j >= k) break;
     const float4 pt = __ldg(cloud + key_idx(keys[j]));
     mean[0] = dadd(mean[0], (double)pt.x);
     mean[1] = dadd(mean[1], (double)pt.y);
@@ -248,20 +268,24 @@ struct KnnTask {
 
 // k nearest neighbours + covariance of point i of task t (one thread); queued on `unresolved_list` when its k
 // neighbours do not lie within max_rings cells of its grid.
-__device__ __forceinline__ void knn_cov_point(const KnnTask& t, int task_id, int i, int k, double eps, int max_rings,
+template <int KS>
+__device__ __forceinline__ void knn_cov_point(const KnnTask& t, int task_id, int i, int k_, double eps, int max_rings,
                                               int2* __restrict__ unresolved_list, unsigned int* __restrict__ unresolved_count) {
   const GridView& g = t.g;
   const float4* __restrict__ cloud = t.cloud;
   const float4 q = __ldg(cloud + i);
-  unsigned long long keys[kMaxK];
-  for (int j = 0; j < kMaxK; ++j) keys[j] = kInfKey;
+  constexpr int kList = KS > 0 ? KS : kMaxK;
+  const int k = KS > 0 ? KS : k_;
+  unsigned long long keys[kList];
+#pragma unroll
+  for (int j = 0; j < kList; ++j) keys[j] = kInfKey;
   const int cx = cell_coord(q.x, g.ox, g.inv_cell, g.nx);
   const int cy = cell_coord(q.y, g.oy, g.inv_cell, g.ny);
   const int cz = cell_coord(q.z, g.oz, g.inv_cell, g.nz);
   bool resolved = false;
   for (int R = 0;; ++R) {
     if (R > max_rings) break;
-    const float thr = key_d2(keys[k - 1]);
+    const float thr = key_d2(KS > 0 ? keys[kList - 1] : keys[k - 1]);
     const int z0 = max(cz - R, 0), z1 = min(cz + R, g.nz - 1);
     const int y0 = max(cy - R, 0), y1 = min(cy + R, g.ny - 1);
     const int xa = max(cx - R, 0), xb = min(cx + R, g.nx - 1);
@@ -272,15 +296,15 @@ __device__ __forceinline__ void knn_cov_point(const KnnTask& t, int task_id, int
       const bool zface = (z == cz - R) || (z == cz + R);
       for (int y = y0; y <= y1; ++y) {
         const float ly = slab_gap(q.y, g.oy, g.cell, y, y, g.slack);
-        if (fadd(fmul(ly, ly), lz2) > key_d2(keys[k - 1])) continue;
+        if (fadd(fmul(ly, ly), lz2) > key_d2(KS > 0 ? keys[kList - 1] : keys[k - 1])) continue;
         const int row = (z * g.ny + y) * g.nx;
         if (zface || y == cy - R || y == cy + R) {
-          knn_scan(g.pts, __ldg(g.cell_start + row + xa), __ldg(g.cell_start + row + xb + 1), q.x, q.y, q.z, keys, k);
+          knn_scan<KS>(g.pts, __ldg(g.cell_start + row + xa), __ldg(g.cell_start + row + xb + 1), q.x, q.y, q.z, keys, k);
         } else {
           if (cx - R >= 0)
-            knn_scan(g.pts, __ldg(g.cell_start + row + cx - R), __ldg(g.cell_start + row + cx - R + 1), q.x, q.y, q.z, keys, k);
+            knn_scan<KS>(g.pts, __ldg(g.cell_start + row + cx - R), __ldg(g.cell_start + row + cx - R + 1), q.x, q.y, q.z, keys, k);
           if (R > 0 && cx + R <= g.nx - 1)
-            knn_scan(g.pts, __ldg(g.cell_start + row + cx + R), __ldg(g.cell_start + row + cx + R + 1), q.x, q.y, q.z, keys, k);
+            knn_scan<KS>(g.pts, __ldg(g.cell_start + row + cx + R), __ldg(g.cell_start + row + cx + R + 1), q.x, q.y, q.z, keys, k);
         }
       }
     }
@@ -297,7 +321,7 @@ __device__ __forceinline__ void knn_cov_point(const KnnTask& t, int task_id, int
       break;
     }
     ex = fmaxf(ex - g.slack, 0.0f);
-    if (fmul(ex, ex) > key_d2(keys[k - 1])) {
+    if (fmul(ex, ex) > key_d2(KS > 0 ? keys[kList - 1] : keys[k - 1])) {
       resolved = true;
       break;
     }
@@ -306,12 +330,13 @@ __device__ __forceinline__ void knn_cov_point(const KnnTask& t, int task_id, int
     unresolved_list[atomicAdd(unresolved_count, 1u)] = make_int2(task_id, i);
     return;
   }
-  cov_from_keys(cloud, keys, k, t.cov + (size_t)9 * i);
+  cov_from_keys<KS>(cloud, keys, k, t.cov + (size_t)9 * i);
 }
 
 
 
 // every point of every cloud of the batch (blockIdx.y = cloud), on the cloud's FINE grid
+template <int KS>
 __global__ void __launch_bounds__(128) knn_cov_kernel(const KnnTask* __restrict__ tasks, int k, double eps, int max_rings,
                                                       int2* __restrict__ unresolved_list,
                                                       unsigned int* __restrict__ unresolved_count) {
@@ -321,13 +346,14 @@ __global__ void __launch_bounds__(128) knn_cov_kernel(const KnnTask* __restrict_
   // threads take the points in CELL order (the grid is over the same cloud): the lanes of a warp walk the same
   // cells, their loads coalesce and their trip counts agree; the result lands at the point's original index
   const int i = __float_as_int(__ldg(t.g.pts + j).w);
-  knn_cov_point(t, (int)blockIdx.y, i, k, eps, max_rings, unresolved_list, unresolved_count);
+  knn_cov_point<KS>(t, (int)blockIdx.y, i, k, eps, max_rings, unresolved_list, unresolved_count);
 }
 
 // second pass: the points the fine grid could not settle (the sparse far field of a sweep: their 20 neighbours lie
 // metres away, dozens of fine cells) on a COARSE grid over the same cloud (cell x 4: the same ring budget reaches 4x
 // as far for the same number of rows).  The k-NN is exact on either grid, so the result does not depend on which
 // pass settled a point.
+template <int KS>
 __global__ void __launch_bounds__(128) knn_cov_list_kernel(const KnnTask* __restrict__ coarse_tasks, int k, double eps, int max_rings,
                                                            const int2* __restrict__ list, const unsigned int* __restrict__ count,
                                                            int2* __restrict__ unresolved_list,
@@ -335,7 +361,7 @@ __global__ void __launch_bounds__(128) knn_cov_list_kernel(const KnnTask* __rest
   const unsigned int total = *count;
   for (unsigned int w = blockIdx.x * blockDim.x + threadIdx.x; w < total; w += gridDim.x * blockDim.x) {
     const int2 e = list[w];
-    knn_cov_point(coarse_tasks[e.x], e.x, e.y, k, eps, max_rings, unresolved_list, unresolved_count);
+    knn_cov_point<KS>(coarse_tasks[e.x], e.x, e.y, k, eps, max_rings, unresolved_list, unresolved_count);
   }
 }
 
@@ -361,7 +387,7 @@ __global__ void __launch_bounds__(kKnnFbThreads) knn_cov_fallback(const KnnTask*
     for (int j = 0; j < kMaxK; ++j) keys[j] = kInfKey;
     for (int j = threadIdx.x; j < t.g.n; j += kKnnFbThreads) {
       const float4 p = __ldg(t.g.pts + j);
-      knn_offer(keys, k, pack_key(sqdist3(q.x, q.y, q.z, p.x, p.y, p.z), __float_as_int(p.w)));
+      knn_offer<0>(keys, k, pack_key(sqdist3(q.x, q.y, q.z, p.x, p.y, p.z), __float_as_int(p.w)));
     }
     int head = 0;
     for (int r = 0; r < k; ++r) {
@@ -382,7 +408,7 @@ __global__ void __launch_bounds__(kKnnFbThreads) knn_cov_fallback(const KnnTask*
     if (threadIdx.x == 0) {
       unsigned long long out[kMaxK];
       for (int j = 0; j < k; ++j) out[j] = s_keys[j];
-      cov_from_keys(t.cloud, out, k, t.cov + (size_t)9 * i);
+      cov_from_keys<0>(t.cloud, out, k, t.cov + (size_t)9 * i);
     }
     __syncthreads();
   }

@@ -497,10 +497,17 @@ int compute_covariances_batch(b2icp_handle* h, GridSlot* const* gs, const size_t
   // (pageable source: the copy is staged by the driver before the call returns)
   CK(cudaMemcpyAsync(h->knn_tasks.p, tasks.data(), tasks.size() * sizeof(KnnTask), cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemsetAsync(h->knn_counts.p, 0, (2 + (size_t)kMaxBatch) * sizeof(unsigned int), h->stream));
-  knn_cov_kernel<<<dim3((unsigned)((max_n + 127) / 128), (unsigned)count, 1), 128, 0, h->stream>>>(fine, k, h->params.gicp_epsilon, 6,
-                                                                                                 h->unres_list.as<int2>(), c1);
-  knn_cov_list_kernel<<<148 * 8, 128, 0, h->stream>>>(coarse, k, h->params.gicp_epsilon, 8, h->unres_list.as<int2>(), c1,
-                                                      h->knn_list2.as<int2>(), c2);
+  // k = 20 (PCL's default, what the reference runs) has its list in registers; any other k takes the general path
+  const dim3 kgrid((unsigned)((max_n + 127) / 128), (unsigned)count, 1);
+  if (k == 20) {
+    knn_cov_kernel<20><<<kgrid, 128, 0, h->stream>>>(fine, k, h->params.gicp_epsilon, 6, h->unres_list.as<int2>(), c1);
+    knn_cov_list_kernel<20><<<148 * 8, 128, 0, h->stream>>>(coarse, k, h->params.gicp_epsilon, 8, h->unres_list.as<int2>(), c1,
+                                                            h->knn_list2.as<int2>(), c2);
+  } else {
+    knn_cov_kernel<0><<<kgrid, 128, 0, h->stream>>>(fine, k, h->params.gicp_epsilon, 6, h->unres_list.as<int2>(), c1);
+    knn_cov_list_kernel<0><<<148 * 8, 128, 0, h->stream>>>(coarse, k, h->params.gicp_epsilon, 8, h->unres_list.as<int2>(), c1,
+                                                           h->knn_list2.as<int2>(), c2);
+  }
   knn_cov_fallback<<<148 * 4, kKnnFbThreads, 0, h->stream>>>(fine, k, h->params.gicp_epsilon, h->knn_list2.as<int2>(), c2);
   // raw covariances -> U diag(1, 1, eps) U^T, lanes load-balanced over the points of each cloud
   const unsigned int sx = (unsigned int)std::max<size_t>(1, std::min<size_t>((max_n + 127) / 128, (size_t)(148 * 16 + count - 1) / (size_t)count));

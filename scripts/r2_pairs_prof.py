@@ -16,13 +16,21 @@ for x in sw:
     p = R.pinned_empty(x.shape)
     p[:] = x
     pinned.append(p)
-reg = R.Registration(preset=R.PRESET_MAPPER)
 srcs, tgts = pinned[1:], [pinned[0]] + [None] * (P - 1)
-reps = 1 if os.environ.get("NCU") else 4
-for rep in range(reps):
-    t0 = time.perf_counter()
-    rc, res = reg.alignBatch(srcs, tgts, with_fitness=True)
-    dt = time.perf_counter() - t0
-    print(json.dumps({"rep": rep, "rc": rc, "ms": 1e3 * dt, "pairs_per_s": P / dt,
-                      "mean_iterations": float(np.mean([r.iterations for r in res])),
-                      "launches": reg.timing().kernel_launches}), flush=True)
+knobs = [dict(a.split("=") for a in c.split(",") if a) for c in sys.argv[1:]] or [{}]
+for cfg in knobs:
+    for k in ("B2ICP_FITNESS_RINGS",):
+        os.environ.pop(k, None)
+    for k, v in cfg.items():
+        os.environ["B2ICP_" + k] = v
+    reg = R.Registration(preset=R.PRESET_MAPPER)
+    reps = 1 if os.environ.get("NCU") else 4
+    for rep in range(reps):
+        t0 = time.perf_counter()
+        rc, res = reg.alignBatch(srcs, tgts, with_fitness=True)
+        dt = time.perf_counter() - t0
+        print(json.dumps({"cfg": cfg, "rep": rep, "rc": rc, "ms": 1e3 * dt, "pairs_per_s": P / dt,
+                          "mean_iterations": float(np.mean([r.iterations for r in res])),
+                          "fitness_sum": float(np.sum([r.fitness for r in res])),
+                          "launches": reg.timing().kernel_launches}), flush=True)
+    del reg
