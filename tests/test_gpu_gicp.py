@@ -107,3 +107,35 @@ def test_gicp_batch_equals_single_calls(R, oracle):
     reg.setInputTarget(sw[0])
     rc, res2 = reg.alignBatch([sw[1], sw[1]], None)
     assert rc == 0 and np.array_equal(res2[0].matrix(), res[0].matrix()) and np.array_equal(res2[1].matrix(), res[0].matrix())
+
+
+def test_concurrent_handles_are_independent(R):
+    """Four host threads, each with its own handle, run batches at once (what bench.py's concurrent GICP leg does, and
+    what a node with several registration clients would): every result equals the one the same call gives alone —
+    GICP (fibers, grouped rounds on private streams, pinned read-backs) and point-to-point alike."""
+    import threading
+    _, _, sw = synth.sweep_sequence(3, 6, n_beams=64, n_az=128)
+    jobs = [(R.MODE_GICP_BFGS, sw[1:4]), (R.MODE_P2P_SVD, sw[2:5]), (R.MODE_GICP_BFGS, sw[3:6]), (R.MODE_P2P_SVD, sw[1:6])]
+
+    def run(mode, clouds):
+        reg = R.Registration(preset=R.PRESET_ODOMETER, mode=mode)
+        reg.setInputTarget(sw[0])
+        rc, res = reg.alignBatch(list(clouds), None, with_fitness=True)
+        return rc, [(r.matrix().copy(), r.iterations, r.converged, r.fitness) for r in res]
+
+    alone = [run(m, c) for m, c in jobs]
+    for _ in range(2):
+        got = [None] * len(jobs)
+
+        def worker(k):
+            got[k] = run(*jobs[k])
+
+        ths = [threading.Thread(target=worker, args=(k,)) for k in range(len(jobs))]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        for a, g in zip(alone, got):
+            assert g is not None and a[0] == g[0] == 0 and len(a[1]) == len(g[1])
+            for (Ta, ia, ca, fa), (Tg, ig, cg, fg) in zip(a[1], g[1]):
+                assert np.array_equal(Ta, Tg) and ia == ig and ca == cg and fa == fg
