@@ -1,5 +1,5 @@
 #!/bin/bash
-# A/B of a tuning knob on the bench's streamed leg: r2_gpu_check15.sh "ENV=1" ...
+# A/B of a tuning knob on the bench's streamed leg: r2_gpu_ab_env.sh "ENV=1" ...
 set -u
 mkdir -p gpurun_out
 for cfg in "$@"; do

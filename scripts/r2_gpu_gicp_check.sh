@@ -10,4 +10,4 @@ for g in ${GROUPS_LIST:-2 4}; do
 import json;d=json.load(open('gpurun_out/gicp_g$g.json'));print($g,{k:round(v.get('scans_per_s',v.get('pairs_per_s'))) for k,v in d.items()})"
   grep -B4 "GICP batch of 32" gpurun_out/gicp_g$g.err | sed -n 6,10p
 done
-bash scripts/r2_gpu_check21.sh | tail -10
+bash scripts/r2_gpu_gicp_knn_launches.sh | tail -10
