@@ -10,11 +10,15 @@
 
 namespace b2 {
 
+// CTA shape of the fused sweep (and of the search kernels that share its scratch layout).  Measured on B200, streamed
+// leg of bench.py (scans/s): 256 threads x 3 CTAs/SM (80 registers, the round-1 shape) 21 674; 128 x 6 (80 registers)
+// 21 972; 128 x 5 (96 registers, no spills, 20 warps/SM) 22 130; 192 x 3 (96 registers, 18 warps/SM) 20 984.  At 80
+// registers the search loop re-materialises addresses and re-reads pointers on every trip; 96 is where that stops.
 #ifndef B2_SWEEP_THREADS
-#define B2_SWEEP_THREADS 256
+#define B2_SWEEP_THREADS 128
 #endif
 #ifndef B2_SWEEP_MIN_CTAS
-#define B2_SWEEP_MIN_CTAS 3
+#define B2_SWEEP_MIN_CTAS 5
 #endif
 #ifndef B2_PHASE_A_UNROLL
 #define B2_PHASE_A_UNROLL 1
