@@ -1,11 +1,13 @@
 // coop.cuh — warp-cooperative exact nearest-neighbour search over TMA-staged candidate tiles.
 //
-// Replaces the per-lane box scan of nncache.cuh inside the ICP sweep and the stand-alone search
-// (pcl::KdTreeFLANN::nearestKSearch(k = 1) as reached from icp.align(), reference
-// src/icpslam/icp_odometer.cpp:198, src/icpslam/octree_mapper.cpp:114).
+// The stand-alone search (pcl::KdTreeFLANN::nearestKSearch(k = 1) as reached from icp.align(), reference
+// src/icpslam/icp_odometer.cpp:198, src/icpslam/octree_mapper.cpp:114; also K9's
+// approxNearestNeighbors in exact mode): nnsearch.cuh drives it.  Inside the ICP loop the per-lane box scan of
+// nncache.cuh stays: there the cached-neighbour certificate has already removed 80 % of the searches and what is left
+// is too sparse to share candidates (measured: DESIGN.md section 4, profiles/r02_coop_sweep_*).
 //
-// The queries a warp has to search are close together (the batch's entry array is ordered by target tile,
-// sort.cuh).  Instead of every lane walking its own cells through dependent global loads, a GROUP of W lanes
+// The queries a warp has to search are close together (large query clouds are counting-sorted by target cell
+// first, b2icp.cu: nn_search_impl).  Instead of every lane walking its own cells through dependent global loads, a GROUP of W lanes
 // (W = 32, or 8 when queries are sparse against the map)
 //   1. takes the union of its lanes' cell boxes.  Cells are x-fastest, so every (y, z) row of the union box is
 //      ONE contiguous run of the sorted target array;
