@@ -9,11 +9,14 @@
 //
 // Batching: the recursion of ONE scan is a chain of ~100 dependent evaluations, each a few microseconds of device
 // work behind a launch and a read-back — latency, not throughput.  A batch therefore runs every scan's recursion
-// as its own FIBER (a private stack and a register switch): the unmodified blocking code of one scan runs until it needs an evaluation, posts
-// its request (new correspondences and / or one cost-functor evaluation) and yields; when every live fiber has
-// yielded, the coordinator serves the whole round with one launch per kernel (blockIdx.y = scan), one 14-double
-// read-back per scan and ONE synchronisation, then resumes the fibers.  A scan's arithmetic does not depend on
-// which other scans share its rounds: results are bit-identical to the one-scan-at-a-time path of round 1.
+// as its own FIBER (a private stack and a register switch): the unmodified blocking code of one scan runs until it
+// needs an evaluation, posts its request (new correspondences and / or one cost-functor evaluation) and yields.  The
+// scans of a batch are dealt to up to kGicpGroups GROUPS, each with its own stream: when every live fiber of a group
+// has yielded, the coordinator serves the group's round — the cost functor of all its scans is ONE launch (tasks as a
+// kernel parameter, blockIdx.y = scan, the 14 sums of a scan written into mapped pinned memory by its last CTA) — and
+// goes on to the next group's fibers while the device works; it comes back, waits for the round's stream and resumes
+// the group's fibers.  A scan's arithmetic does not depend on which other scans share its rounds or its group:
+// results are bit-identical to the one-scan-at-a-time path of round 1.
 struct GicpJob;
 void gicp_yield(GicpJob* job);
 

@@ -112,6 +112,7 @@ def lib() -> C.CDLL:
         L.b2o_covariances.argtypes = [fp, C.c_size_t, C.c_int, C.c_double, dp]
         L.b2o_umeyama.argtypes = [fp, fp, C.c_size_t, dp]
         L.b2o_svd3.argtypes = [dp, dp, dp, dp]
+        L.b2o_svd3_cov.argtypes = [dp, dp, dp, dp]
         L.b2o_align.argtypes = [C.POINTER(Params), fp, C.c_size_t, fp, C.c_size_t, fp, C.POINTER(Result), fp,
                                 C.c_int, ip, fp, C.POINTER(StageMs)]
         L.b2o_fitness.argtypes = [fp, C.c_size_t, fp, C.c_size_t, fp, C.c_double, dp]
@@ -234,12 +235,13 @@ def umeyama(src, dst):
     return T.reshape(4, 4)
 
 
-def svd3(A):
+def svd3(A, cov=False):
+    """One-sided Jacobi SVD of the restatement; cov=True: the pair-skip threshold of the GICP covariances (1e-15)."""
     A = np.ascontiguousarray(A, dtype=np.float64)
     U = np.empty((3, 3))
     s = np.empty(3)
     V = np.empty((3, 3))
-    lib().b2o_svd3(_d(A), _d(U), _d(s), _d(V))
+    (lib().b2o_svd3_cov if cov else lib().b2o_svd3)(_d(A), _d(U), _d(s), _d(V))
     return U, s, V
 
 

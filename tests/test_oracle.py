@@ -73,6 +73,16 @@ def test_svd3_and_umeyama_kats(oracle):
         assert np.abs(U @ np.diag(s) @ V.T - A).max() < 1e-13
         assert np.abs(s - np.linalg.svd(A)[1]).max() < 1e-13
         assert np.abs(U.T @ U - np.eye(3)).max() < 1e-13 and np.abs(V.T @ V - np.eye(3)).max() < 1e-13
+    # the GICP covariances run the same recipe with the pair-skip threshold at 1e-15 (where a rotation stops changing
+    # an fp64 column; the device kernel restates exactly this): symmetric PSD inputs, as accurate as the 1e-17 variant
+    for _ in range(20):
+        B = rng.normal(size=(3, 20))
+        Cm = np.cov(B) * rng.uniform(1e-4, 10.0)
+        U, s, V = oracle.svd3(Cm, cov=True)
+        assert np.abs(U @ np.diag(s) @ V.T - Cm).max() < 1e-13 * max(1.0, s[0])
+        assert np.abs(s - np.linalg.svd(Cm)[1]).max() < 1e-13 * max(1.0, s[0])
+        U17 = oracle.svd3(Cm)[0]
+        assert np.abs(np.abs(U.T @ U17) - np.eye(3)).max() < 1e-6   # same singular vectors up to sign
     A = np.outer([1, 2, 3], [4, 5, 6.0])          # rank 1
     U, s, V = oracle.svd3(A)
     assert np.abs(U @ np.diag(s) @ V.T - A).max() < 1e-12 and abs(abs(np.linalg.det(U)) - 1) < 1e-12
