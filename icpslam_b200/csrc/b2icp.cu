@@ -274,7 +274,7 @@ struct b2icp_handle {
   size_t h_gicp_partials_cap = 0;
   void* h_gicp_tasks = nullptr;  // pinned task arrays of a GICP round (gicp_host.inl)
   size_t h_gicp_tasks_cap = 0;
-  DeviceBuf gicp_tasks, gicp_sums, knn_tasks, knn_list2, knn_counts;
+  DeviceBuf gicp_tasks, gicp_tickets, knn_tasks, knn_list2, knn_counts;
   long gicp_evals = 0, gicp_rounds = 0;
   int gicp_groups = 4;  // B2ICP_GICP_GROUPS (tuning only)
   int fitness_rings = kUnboundedRings;  // B2ICP_FITNESS_RINGS (tuning only): ring budget of getFitnessScore's search
@@ -1211,7 +1211,7 @@ int b2icp_destroy(b2icp_handle* h) {
   if (h->h_gicp_partials) cudaFreeHost(h->h_gicp_partials);
   if (h->h_gicp_tasks) cudaFreeHost(h->h_gicp_tasks);
   h->tiny_partials.release();
-  for (DeviceBuf* b : {&h->gicp_tasks, &h->gicp_sums, &h->knn_tasks, &h->knn_list2, &h->knn_counts}) b->release();
+  for (DeviceBuf* b : {&h->gicp_tasks, &h->gicp_tickets, &h->knn_tasks, &h->knn_list2, &h->knn_counts}) b->release();
   if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
   return B2ICP_OK;

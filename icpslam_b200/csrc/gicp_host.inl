@@ -812,9 +812,9 @@ int run_gicp_batch(b2icp_handle* h, int B, const float* guesses) {
     h->h_gicp_partials_cap = kTaskSlots * kGicpSums;
   }
   CK(h->gicp_tasks.ensure(task_bytes));
-  if (!h->gicp_sums.p) {  // per-scan tickets of the cost-functor kernel's last-CTA sum: zero between launches
-    CK(h->gicp_sums.ensure((size_t)kMaxBatch * sizeof(unsigned int)));
-    CK(cudaMemsetAsync(h->gicp_sums.p, 0, (size_t)kMaxBatch * sizeof(unsigned int), h->stream));
+  if (!h->gicp_tickets.p) {  // per-scan tickets of the cost-functor kernel's last-CTA sum: zero between launches
+    CK(h->gicp_tickets.ensure((size_t)kMaxBatch * sizeof(unsigned int)));
+    CK(cudaMemsetAsync(h->gicp_tickets.p, 0, (size_t)kMaxBatch * sizeof(unsigned int), h->stream));
   }
   GicpCorrTask* h_corr = reinterpret_cast<GicpCorrTask*>(h->h_gicp_tasks);
   GicpCorrTask* d_corr = h->gicp_tasks.as<GicpCorrTask>();
@@ -943,7 +943,7 @@ int run_gicp_batch(b2icp_handle* h, int B, const float* guesses) {
         t.mahal = s.mahal.as<double>();
         t.partials = s.gicp_partials.as<double>();
         t.sums = h->h_gicp_partials + (off + (size_t)(k0 + k)) * kGicpSums;
-        t.ticket = h->gicp_sums.as<unsigned int>() + i;
+        t.ticket = h->gicp_tickets.as<unsigned int>() + i;
         t.n = (int)s.src.n;
         t.pad = 0;
         t.a = jobs[i]->eval;
