@@ -25,7 +25,7 @@ def _nvcc() -> str:
 
 
 def sources() -> list[str]:
-    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".inl")))
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".inl", ".h")))
 
 
 def is_stale() -> bool:

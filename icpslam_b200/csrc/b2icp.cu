@@ -12,39 +12,7 @@
 #include "../../include/b2icp.h"
 
 #include <cuda_runtime.h>
-#include <ucontext.h>
-
-// Fiber switch of the GICP host loop (gicp_host.inl).  swapcontext() saves and restores the signal mask: two system
-// calls per switch, ~0.3 us each way, which was two thirds of the host time of a GICP round.  On x86-64 the switch
-// is six callee-saved registers and the stack pointer; elsewhere the ucontext path stays.
-#if defined(__x86_64__) && !defined(B2_FIBER_UCONTEXT) && !defined(__CUDA_ARCH__)
-#define B2_FIBER_ASM 1
-extern "C" void b2_fiber_switch(void** save_sp, void* load_sp);
-asm(R"(
-.text
-.p2align 4
-.globl b2_fiber_switch
-.hidden b2_fiber_switch
-.type b2_fiber_switch,@function
-b2_fiber_switch:
-    pushq %rbp
-    pushq %rbx
-    pushq %r12
-    pushq %r13
-    pushq %r14
-    pushq %r15
-    movq %rsp, (%rdi)
-    movq %rsi, %rsp
-    popq %r15
-    popq %r14
-    popq %r13
-    popq %r12
-    popq %rbx
-    popq %rbp
-    ret
-.size b2_fiber_switch,.-b2_fiber_switch
-)");
-#endif
+#include "fiber.h"
 
 #include <algorithm>
 #include <cfloat>

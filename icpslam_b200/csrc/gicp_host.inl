@@ -20,34 +20,6 @@
 struct GicpJob;
 void gicp_yield(GicpJob* job);
 
-// One execution context of the host loop: the coordinator's or a scan's fiber.
-#ifdef B2_FIBER_ASM
-struct FiberCtx {
-  void* sp = nullptr;
-};
-inline void fiber_switch(FiberCtx& from, FiberCtx& to) { b2_fiber_switch(&from.sp, to.sp); }
-// first switch into `c` "returns" into entry() on the given stack (entry never returns: it switches away for good)
-inline void fiber_make(FiberCtx& c, FiberCtx&, char* stack, size_t size, void (*entry)()) {
-  void** sp = reinterpret_cast<void**>((reinterpret_cast<uintptr_t>(stack) + size) & ~(uintptr_t)15);
-  *--sp = nullptr;                              // where entry's return address would be
-  *--sp = reinterpret_cast<void*>(entry);       // popped by the switch's `ret`; entry then sees rsp = 8 mod 16
-  for (int i = 0; i < 6; ++i) *--sp = nullptr;  // rbp rbx r12 r13 r14 r15
-  c.sp = sp;
-}
-#else
-struct FiberCtx {
-  ucontext_t uc;
-};
-inline void fiber_switch(FiberCtx& from, FiberCtx& to) { swapcontext(&from.uc, &to.uc); }
-inline void fiber_make(FiberCtx& c, FiberCtx& back, char* stack, size_t size, void (*entry)()) {
-  getcontext(&c.uc);
-  c.uc.uc_stack.ss_sp = stack;
-  c.uc.uc_stack.ss_size = size;
-  c.uc.uc_link = &back.uc;
-  makecontext(&c.uc, entry, 0);
-}
-#endif
-
 struct GicpHostFunctor {
   b2icp_handle* h;
   ScanSlot* s;

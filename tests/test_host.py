@@ -153,6 +153,19 @@ def test_shims_compile_and_pose_selfcheck(b2lib, tmp_path):
         assert r.returncode == 3 and "CUDA" in r.stderr
 
 
+@pytest.mark.parametrize("flags", [[], ["-DB2_FIBER_UCONTEXT"]], ids=["register-switch", "ucontext"])
+def test_gicp_fibers_interleave_without_disturbing_each_other(tmp_path, flags):
+    """The batched GICP host loop runs every scan's blocking recursion on its own fiber (icpslam_b200/csrc/fiber.h): 32
+    fibers doing floating-point and libc work between different numbers of yields, interleaved by a coordinator, end
+    with bitwise the results of the same work done straight — for the six-register switch and for its fallback."""
+    exe = str(tmp_path / "fiber_test")
+    subprocess.run(["/usr/bin/g++", "-O2", "-std=c++17", *flags, "-o", exe, os.path.join(ROOT, "tests", "cpp", "fiber_test.cpp")],
+                   check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "bad=0" in r.stdout, r.stdout + r.stderr
+    assert ("ucontext" in r.stdout) == bool(flags) or os.uname().machine != "x86_64"
+
+
 def test_bench_reference_arm_prints_the_contract_line():
     """`bench.py --impl reference` (the oracle timed on the host cores, no GPU, nothing read from /root/reference)
     prints one JSON line with the keys the driver reads."""
