@@ -518,32 +518,37 @@ def main():
         # the same call from GICP_CALLERS host threads at once, each with its own handle and its own set of 32 sweeps
         # (the four noise variants): a batch's rounds leave the device idle between launches and its set-up leaves the
         # host idle, so concurrent callers fill both — the counterpart of the 8 batches in flight of the main leg
-        handles = [greg] + [R.Registration(preset=R.PRESET_MAPPER, mode=R.MODE_GICP_BFGS, device=local_rank)
-                            for _ in range(GICP_CALLERS - 1)]
-        for g in handles[1:]:
-            g.setInputTarget(map_xyzw)
-        outs = [None] * GICP_CALLERS
+        try:  # an auxiliary record: a failure here must not cost the bench line
+            handles = [greg] + [R.Registration(preset=R.PRESET_MAPPER, mode=R.MODE_GICP_BFGS, device=local_rank)
+                                for _ in range(GICP_CALLERS - 1)]
+            for g in handles[1:]:
+                g.setInputTarget(map_xyzw)
+            outs = [None] * GICP_CALLERS
 
-        def caller(k):
-            torch.cuda.set_device(local_rank)
-            outs[k] = handles[k].alignBatch(h_sets[k % N_SETS])
+            def caller(k):
+                torch.cuda.set_device(local_rank)
+                outs[k] = handles[k].alignBatch(h_sets[k % N_SETS])
 
-        def all_callers():
-            ths = [threading.Thread(target=caller, args=(k,)) for k in range(GICP_CALLERS)]
-            t0 = time.perf_counter()
-            for t in ths:
-                t.start()
-            for t in ths:
-                t.join()
-            return time.perf_counter() - t0
+            def all_callers():
+                ths = [threading.Thread(target=caller, args=(k,)) for k in range(GICP_CALLERS)]
+                t0 = time.perf_counter()
+                for t in ths:
+                    t.start()
+                for t in ths:
+                    t.join()
+                if any(o is None for o in outs):
+                    raise RuntimeError("a concurrent GICP caller did not return")
+                return time.perf_counter() - t0
 
-        all_callers()                                  # buffers and target covariances of the extra handles
-        bestc = min(all_callers() for _ in range(2))
-        gicp["concurrent"] = {"callers": GICP_CALLERS, "scans": GICP_CALLERS * Bn,
-                              "scans_per_s": GICP_CALLERS * Bn / bestc, "ms_total": 1e3 * bestc,
-                              "rc": [int(o[0]) for o in outs],
-                              "converged": int(sum(r.converged for o in outs for r in o[1]))}
-        del handles
+            all_callers()                              # buffers and target covariances of the extra handles
+            bestc = min(all_callers() for _ in range(2))
+            gicp["concurrent"] = {"callers": GICP_CALLERS, "scans": GICP_CALLERS * Bn,
+                                  "scans_per_s": GICP_CALLERS * Bn / bestc, "ms_total": 1e3 * bestc,
+                                  "rc": [int(o[0]) for o in outs],
+                                  "converged": int(sum(r.converged for o in outs for r in o[1]))}
+            del handles
+        except Exception as e:  # noqa: BLE001
+            gicp["concurrent"] = {"error": f"{type(e).__name__}: {e}"}
         del greg
     pairs = None
     if not args.no_pairs:
