@@ -166,6 +166,25 @@ def test_gicp_fibers_interleave_without_disturbing_each_other(tmp_path, flags):
     assert ("ucontext" in r.stdout) == bool(flags) or os.uname().machine != "x86_64"
 
 
+def test_ros_adapter_compiles_against_stub_headers(b2lib, tmp_path):
+    """The ROS-facing half of shims/b2icp_ros_adapter.hpp (::IcpOdometer / ::OctreeMapper with the reference's
+    signatures, include/icpslam/icp_odometer.h:30-58, octree_mapper.h:23-49) only exists behind __has_include(<ros/ros.h>)
+    and this image has no ROS: it is compiled here against minimal stand-in headers (tests/cpp/ros_stubs) with every
+    adapter method referenced through the reference's argument types, and linked against libb2icp.so.  Without a GPU
+    the constructed odometer must fail loudly (no CPU path behind the adapter either)."""
+    from icpslam_b200 import build as B
+    exe = str(tmp_path / "ros_adapter")
+    cmd = ["/usr/bin/g++", "-O1", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "tests", "cpp", "ros_stubs"), "-o", exe,
+           os.path.join(ROOT, "tests", "cpp", "ros_adapter_compile.cpp"), "-L", B.LIB_DIR, "-lb2icp", f"-Wl,-rpath,{B.LIB_DIR}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert subprocess.run([exe], capture_output=True, text=True).stdout.strip() == "compiled"
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe, "run"], capture_output=True, text=True)
+        assert r.returncode == 3 and "CUDA" in r.stderr
+
+
 def test_bench_reference_arm_prints_the_contract_line():
     """`bench.py --impl reference` (the oracle timed on the host cores, no GPU, nothing read from /root/reference)
     prints one JSON line with the keys the driver reads."""
