@@ -14,8 +14,11 @@
  * Matrices: every 4x4 in this ABI is ROW-MAJOR (T[4*r+c]); p_target = T * p_source.
  *
  * Threading: calls on one handle are serialised by an internal mutex; distinct handles are
- * independent (own CUDA stream).  All entry points are synchronous (results are in the caller's
- * buffers on return) because the reference consumes T immediately (icp_odometer.cpp:199-206).
+ * independent (own CUDA streams, device buffers and pinned memory) and may be driven from
+ * different host threads at the same time.  Entry points are synchronous (results are in the
+ * caller's buffers on return) because the reference consumes T immediately
+ * (icp_odometer.cpp:199-206); the exception is the pair b2icp_align_batch_submit[_device] /
+ * b2icp_align_batch_wait, which keeps several batches in flight for offline replay.
  *
  * There is NO CPU backend behind these symbols: without a CUDA device b2icp_create fails with
  * B2ICP_ERR_CUDA.  (The CPU restatement under oracle/ is test infrastructure only.)
